@@ -1,0 +1,37 @@
+"""Build libnlf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+-fmad=false : the path is bit-exact fp64 in the reference's operation order; no contraction.
+-lineinfo   : ncu source pages map to the .cu files.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libnlf_b200.so")
+SOURCES = ["score.cu", "norm.cu", "pool.cu"]
+
+
+def _newest_source_mtime() -> float:
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "nlf_b200.h")]
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source_mtime():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-o", OUT]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,158 @@
+// common.cuh -- shared host/device plumbing of libnlf_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nlf_b200.h"
+
+#define NLF_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace nlf {
+
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define NLF_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return nlf::fail(NLF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                             cudaGetErrorString(e__));                                              \
+    } while (0)
+
+enum ProfClass { P_BANDIFY = 0, P_DIAG = 1, P_FEATURE = 2, P_FOREST = 3, P_THRESH = 4, P_NORM = 5, P_POOL = 6, P_NCLASS = 8 };
+
+}  // namespace nlf
+
+struct nlf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    long long launches = 0;
+    bool profile = false;
+    // profiling: (class, start, stop) triples recorded in-stream, resolved lazily
+    struct Rec { int cls; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> free_events;
+    float prof_ms[nlf::P_NCLASS] = {0};
+    long long prof_n[nlf::P_NCLASS] = {0};
+    int sm_count = 148;
+
+    cudaEvent_t get_event()
+    {
+        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_begin(int cls, cudaEvent_t *a)
+    {
+        launches++;
+        if (!profile) return;
+        *a = get_event();
+        cudaEventRecord(*a, stream);
+        (void)cls;
+    }
+    void prof_end(int cls, cudaEvent_t a)
+    {
+        if (!profile) return;
+        cudaEvent_t b = get_event();
+        cudaEventRecord(b, stream);
+        recs.push_back({cls, a, b});
+    }
+    void prof_resolve()
+    {
+        for (auto &r : recs) {
+            float ms = 0;
+            cudaEventSynchronize(r.b);
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            prof_ms[r.cls] += ms;
+            prof_n[r.cls] += 1;
+            free_events.push_back(r.a);
+            free_events.push_back(r.b);
+        }
+        recs.clear();
+    }
+};
+
+// RAII-free helper: launch bracket used as  { KLaunch k(ctx, cls); kernel<<<...>>>(...); }
+struct KLaunch {
+    nlf_ctx *c; int cls; cudaEvent_t a = nullptr;
+    KLaunch(nlf_ctx *ctx, int cls_) : c(ctx), cls(cls_) { c->prof_begin(cls, &a); }
+    ~KLaunch() { c->prof_end(cls, a); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers shared by the kernels: numpy's pairwise summation, exactly
+// (numpy/_core/src/umath/loops_utils.h.src DOUBLE_pairwise_sum), no FMA, no reassociation.
+// ---------------------------------------------------------------------------------------------
+namespace nlf {
+
+template <typename Load>
+__device__ __forceinline__ double np_leaf_sum(Load ld, int off, int n)
+{
+    if (n < 8) {
+        double r = -0.0;
+        for (int i = 0; i < n; i++) r = __dadd_rn(r, ld(off + i));
+        return r;
+    }
+    double r0 = ld(off + 0), r1 = ld(off + 1), r2 = ld(off + 2), r3 = ld(off + 3);
+    double r4 = ld(off + 4), r5 = ld(off + 5), r6 = ld(off + 6), r7 = ld(off + 7);
+    int i;
+    int lim = n - (n % 8);
+    for (i = 8; i < lim; i += 8) {
+        double a0 = ld(off + i + 0), a1 = ld(off + i + 1), a2 = ld(off + i + 2), a3 = ld(off + i + 3);
+        double a4 = ld(off + i + 4), a5 = ld(off + i + 5), a6 = ld(off + i + 6), a7 = ld(off + i + 7);
+        r0 = __dadd_rn(r0, a0); r1 = __dadd_rn(r1, a1); r2 = __dadd_rn(r2, a2); r3 = __dadd_rn(r3, a3);
+        r4 = __dadd_rn(r4, a4); r5 = __dadd_rn(r5, a5); r6 = __dadd_rn(r6, a6); r7 = __dadd_rn(r7, a7);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; i < n; i++) res = __dadd_rn(res, ld(off + i));
+    return res;
+}
+
+// sum of ld(0..n-1) in numpy's pairwise order (recursion made explicit; depth <= 24)
+template <typename Load>
+__device__ double np_pairwise_sum(Load ld, int n)
+{
+    if (n <= 128) return np_leaf_sum(ld, 0, n);
+    int st_off[48], st_n[48];   // st_n < 0 marks a "combine" entry
+    double vs[26];
+    int sp = 0, vp = 0;
+    st_off[sp] = 0; st_n[sp] = n; sp++;
+    while (sp) {
+        sp--;
+        int o = st_off[sp], m = st_n[sp];
+        if (m < 0) {
+            double r = vs[--vp];
+            double l = vs[--vp];
+            vs[vp++] = __dadd_rn(l, r);
+        } else if (m <= 128) {
+            vs[vp++] = np_leaf_sum(ld, o, m);
+        } else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            st_off[sp] = 0; st_n[sp] = -1; sp++;
+            st_off[sp] = o + n2; st_n[sp] = m - n2; sp++;
+            st_off[sp] = o; st_n[sp] = n2; sp++;
+        }
+    }
+    return vs[0];
+}
+
+}  // namespace nlf

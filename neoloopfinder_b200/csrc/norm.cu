@@ -1,0 +1,338 @@
+// norm.cu -- distance normalisation of one SV-assembly matrix on B200 (sm_100a):
+//   K2 masked per-diagonal means per block pair, numpy summation order   (callers.py:348-367,
+//                                                                         assembly.py:497-516)
+//   K3 per-block-pair rescale                                            (assembly.py:536-557)
+//   K4 gap columns (column sums in numpy's row order) + gap-free band    (callers.py:504-522)
+// The regression between K2 and K3 (callers.py:370-412: Spearman + isotonic + Huber/L-BFGS on
+// <= 400 points per pair) stays on the host; this file moves every pass over the n x n matrix.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace nlf;
+
+struct nlf_assembly {
+    nlf_ctx *ctx = nullptr;
+    int n = 0, nblk = 0;
+    double *d_M = nullptr, *d_bias = nullptr, *d_val = nullptr;
+    int *d_blk = nullptr, *d_op = nullptr, *d_kept = nullptr;
+    std::vector<int> blo, bhi, kept;
+    bool scales_set = false, gaps_done = false;
+};
+
+// value of hcm[r][c] = fusion_matrix[r][c] rescaled by the rule of its block pair
+__device__ __forceinline__ double scaled_value(const double *__restrict__ M, int n, const int *__restrict__ blk,
+                                               const int *__restrict__ op, const double *__restrict__ val, int nblk,
+                                               int r, int c)
+{
+    double v = M[(size_t)r * n + c];
+    int p = blk[r] * nblk + blk[c];
+    int o = op[p];
+    if (o == 1) v = __ddiv_rn(v, val[p]);
+    else if (o == 2) v = __dmul_rn(v, val[p]);
+    return v;
+}
+
+// K2a: one thread per (pair, diagonal): gather the valid pixels in row order into scratch.
+// scratch[k * stride + pair*(maxdiag+1) + i] so that neighbouring diagonals are neighbours in memory.
+__global__ void k_pair_compact(const double *__restrict__ M, int n, const double *__restrict__ bias,
+                               const int *__restrict__ pair_lo1, const int *__restrict__ pair_hi1,
+                               const int *__restrict__ pair_lo2, const int *__restrict__ pair_hi2, int npairs,
+                               int maxdiag, double *__restrict__ scratch, size_t stride, int *__restrict__ cnt)
+{
+    int p = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > maxdiag) return;
+    int idx = p * (maxdiag + 1) + i;
+    int k = 0;
+    if (i >= 2 && i < n - 1) {          // for i in range(2, M.shape[0]-1)
+        int lo1 = pair_lo1[p], hi1 = pair_hi1[p], lo2 = pair_lo2[p], hi2 = pair_hi2[p];
+        int xs = max(lo1, lo2 - i), xe = min(hi1, min(hi2, n) - i);
+        for (int x = xs; x < xe; x++) {
+            int y = x + i;
+            if (__dmul_rn(bias[x], bias[y]) > 0) {
+                scratch[(size_t)k * stride + idx] = M[(size_t)x * n + y];
+                k++;
+            }
+        }
+    }
+    cnt[idx] = k;
+}
+
+// K2b: numpy mean of the gathered values
+__global__ void k_pair_means(const double *__restrict__ scratch, size_t stride, const int *__restrict__ cnt,
+                             int total, int mink, double *__restrict__ mean)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c = cnt[idx];
+    double m = __longlong_as_double(0x7ff8000000000000LL);
+    if (c >= mink && c > 0) {
+        const double *base = scratch + idx;
+        double s = np_pairwise_sum([=](int k) { return base[(size_t)k * stride]; }, c);
+        double mm = __ddiv_rn(s, (double)c);
+        if (mm > 0) m = mm;
+    }
+    mean[idx] = m;
+}
+
+// K4a: column sums of hcm in numpy's axis-0 order (row after row), one thread per column.
+__global__ void k_gap_columns(const double *__restrict__ M, int n, const int *__restrict__ blk,
+                              const int *__restrict__ op, const double *__restrict__ val, int nblk,
+                              unsigned char *__restrict__ is_gap)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = scaled_value(M, n, blk, op, val, nblk, 0, j);
+    int r = 1;
+    for (; r + 4 <= n; r += 4) {
+        double a0 = scaled_value(M, n, blk, op, val, nblk, r, j);
+        double a1 = scaled_value(M, n, blk, op, val, nblk, r + 1, j);
+        double a2 = scaled_value(M, n, blk, op, val, nblk, r + 2, j);
+        double a3 = scaled_value(M, n, blk, op, val, nblk, r + 3, j);
+        s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, a0), a1), a2), a3);
+    }
+    for (; r < n; r++) s = __dadd_rn(s, scaled_value(M, n, blk, op, val, nblk, r, j));
+    is_gap[j] = (s == 0) ? 1 : 0;
+}
+
+// K4b: gap-free band straight from the fusion matrix: band[i][d] = hcm[kept[i]][kept[i+d]]
+__global__ void k_gap_band(const double *__restrict__ M, int n, const int *__restrict__ blk,
+                           const int *__restrict__ op, const double *__restrict__ val, int nblk,
+                           const int *__restrict__ kept, int nk, int bw, int pitch, double *__restrict__ band)
+{
+    int i = blockIdx.y;
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= pitch) return;
+    double v = 0.0;
+    if (d < bw && i + d < nk) {
+        v = scaled_value(M, n, blk, op, val, nblk, kept[i], kept[i + d]);
+        if (!isfinite(v)) v = 0.0;
+    }
+    band[(size_t)i * pitch + d] = v;
+}
+
+// dense outputs for the public attributes complexSV.hcm / Fusion.gap_free
+__global__ void k_dense_out(const double *__restrict__ M, int n, const int *__restrict__ blk,
+                            const int *__restrict__ op, const double *__restrict__ val, int nblk,
+                            const int *__restrict__ kept, int nk, double *__restrict__ out)
+{
+    int i = blockIdx.y;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nk) return;
+    int r = kept ? kept[i] : i, c = kept ? kept[j] : j;
+    out[(size_t)i * nk + j] = scaled_value(M, n, blk, op, val, nblk, r, c);
+}
+
+NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const double *bias, const int *blk_lo,
+                                   const int *blk_hi, int nblk, nlf_assembly **out)
+{
+    if (!ctx || !M || !bias || !blk_lo || !blk_hi || !out || n <= 0 || nblk <= 0)
+        return fail(NLF_ERR_ARG, "nlf_assembly_create: bad arguments");
+    if (n > 65535) return fail(NLF_ERR_ARG, "assembly of %d bins exceeds the dense limit 65535", n);
+    std::vector<int> blk(n, -1);
+    for (int b = 0; b < nblk; b++) {
+        if (blk_lo[b] < 0 || blk_hi[b] > n || blk_lo[b] > blk_hi[b])
+            return fail(NLF_ERR_ARG, "block %d range [%d,%d) outside [0,%d)", b, blk_lo[b], blk_hi[b], n);
+        for (int r = blk_lo[b]; r < blk_hi[b]; r++) blk[r] = b;
+    }
+    for (int r = 0; r < n; r++)
+        if (blk[r] < 0) return fail(NLF_ERR_ARG, "bin %d belongs to no block", r);
+    NLF_CUDA(cudaSetDevice(ctx->device));
+    nlf_assembly *a = new nlf_assembly();
+    a->ctx = ctx; a->n = n; a->nblk = nblk;
+    a->blo.assign(blk_lo, blk_lo + nblk);
+    a->bhi.assign(blk_hi, blk_hi + nblk);
+    cudaStream_t s = ctx->stream;
+    NLF_CUDA(cudaMallocAsync(&a->d_M, sizeof(double) * (size_t)n * n, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_bias, sizeof(double) * n, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_blk, sizeof(int) * n, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_op, sizeof(int) * nblk * nblk, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_val, sizeof(double) * nblk * nblk, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_kept, sizeof(int) * n, s));
+    NLF_CUDA(cudaMemcpyAsync(a->d_M, M, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(a->d_blk, blk.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemsetAsync(a->d_op, 0, sizeof(int) * nblk * nblk, s));
+    NLF_CUDA(cudaMemsetAsync(a->d_val, 0, sizeof(double) * nblk * nblk, s));
+    *out = a;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_diag_means(nlf_assembly *a, int maxdiag, int mink, double *mean_out, int *cnt_out)
+{
+    if (!a || maxdiag < 0 || !mean_out || !cnt_out) return fail(NLF_ERR_ARG, "nlf_assembly_diag_means: bad arguments");
+    nlf_ctx *c = a->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int nb = a->nblk, npairs = nb * (nb + 1) / 2, nd = maxdiag + 1;
+    std::vector<int> lo1, hi1, lo2, hi2;
+    int maxlen = 1;
+    for (int j1 = 0; j1 < nb; j1++)
+        for (int j2 = j1; j2 < nb; j2++) {
+            lo1.push_back(a->blo[j1]); hi1.push_back(a->bhi[j1]);
+            lo2.push_back(a->blo[j2]); hi2.push_back(a->bhi[j2]);
+            maxlen = std::max(maxlen, a->bhi[j1] - a->blo[j1]);
+        }
+    const int total = npairs * nd;
+    const size_t stride = (size_t)total;
+    int *d_par, *d_cnt;
+    double *d_scratch, *d_mean;
+    NLF_CUDA(cudaMallocAsync(&d_par, sizeof(int) * 4 * npairs, s));
+    NLF_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * total, s));
+    NLF_CUDA(cudaMallocAsync(&d_mean, sizeof(double) * total, s));
+    NLF_CUDA(cudaMallocAsync(&d_scratch, sizeof(double) * stride * maxlen, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par, lo1.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par + npairs, hi1.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par + 2 * npairs, lo2.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par + 3 * npairs, hi2.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
+    {
+        KLaunch k(c, P_NORM);
+        dim3 grid((nd + 63) / 64, npairs);
+        k_pair_compact<<<grid, 64, 0, s>>>(a->d_M, a->n, a->d_bias, d_par, d_par + npairs, d_par + 2 * npairs,
+                                           d_par + 3 * npairs, npairs, maxdiag, d_scratch, stride, d_cnt);
+    }
+    {
+        KLaunch k(c, P_NORM);
+        k_pair_means<<<(total + 63) / 64, 64, 0, s>>>(d_scratch, stride, d_cnt, total, mink, d_mean);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * total, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaMemcpyAsync(cnt_out, d_cnt, sizeof(int) * total, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    NLF_CUDA(cudaFreeAsync(d_par, s));
+    NLF_CUDA(cudaFreeAsync(d_cnt, s));
+    NLF_CUDA(cudaFreeAsync(d_mean, s));
+    NLF_CUDA(cudaFreeAsync(d_scratch, s));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_set_scales(nlf_assembly *a, const int *op, const double *val)
+{
+    if (!a || !op || !val) return fail(NLF_ERR_ARG, "nlf_assembly_set_scales: NULL argument");
+    nlf_ctx *c = a->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    const int nb2 = a->nblk * a->nblk;
+    std::vector<int> o(op, op + nb2);
+    for (int j1 = 0; j1 < a->nblk; j1++)
+        for (int j2 = 0; j2 < j1; j2++) o[j1 * a->nblk + j2] = 0;   // only j1 <= j2 is ever rescaled
+    NLF_CUDA(cudaMemcpyAsync(a->d_op, o.data(), sizeof(int) * nb2, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(a->d_val, val, sizeof(double) * nb2, cudaMemcpyHostToDevice, c->stream));
+    a->scales_set = true;
+    a->gaps_done = false;
+    return NLF_OK;
+}
+
+static int ensure_gaps(nlf_assembly *a)
+{
+    if (a->gaps_done) return NLF_OK;
+    nlf_ctx *c = a->ctx;
+    cudaStream_t s = c->stream;
+    const int n = a->n;
+    unsigned char *d_gap;
+    NLF_CUDA(cudaMallocAsync(&d_gap, n, s));
+    {
+        KLaunch k(c, P_NORM);
+        k_gap_columns<<<(n + 63) / 64, 64, 0, s>>>(a->d_M, n, a->d_blk, a->d_op, a->d_val, a->nblk, d_gap);
+    }
+    NLF_CUDA(cudaGetLastError());
+    std::vector<unsigned char> gap(n);
+    NLF_CUDA(cudaMemcpyAsync(gap.data(), d_gap, n, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    NLF_CUDA(cudaFreeAsync(d_gap, s));
+    // index bookkeeping of callers.py:509-516 (w = 5: keep every bin when fewer than 11 survive)
+    a->kept.clear();
+    for (int j = 0; j < n; j++)
+        if (!gap[j]) a->kept.push_back(j);
+    if (5 * 2 + 1 > (int)a->kept.size()) {
+        a->kept.resize(n);
+        for (int j = 0; j < n; j++) a->kept[j] = j;
+    }
+    NLF_CUDA(cudaMemcpyAsync(a->d_kept, a->kept.data(), sizeof(int) * a->kept.size(), cudaMemcpyHostToDevice, s));
+    a->gaps_done = true;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_remove_gaps(nlf_assembly *a, int *kept_out, int *n_kept)
+{
+    if (!a || !n_kept) return fail(NLF_ERR_ARG, "nlf_assembly_remove_gaps: NULL argument");
+    NLF_CUDA(cudaSetDevice(a->ctx->device));
+    int rc = ensure_gaps(a);
+    if (rc) return rc;
+    *n_kept = (int)a->kept.size();
+    if (kept_out) memcpy(kept_out, a->kept.data(), sizeof(int) * a->kept.size());
+    return NLF_OK;
+}
+
+static int dense_out(nlf_assembly *a, bool gap_free, double *out)
+{
+    nlf_ctx *c = a->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int nk = a->n;
+    if (gap_free) {
+        int rc = ensure_gaps(a);
+        if (rc) return rc;
+        nk = (int)a->kept.size();
+    }
+    double *d_out;
+    NLF_CUDA(cudaMallocAsync(&d_out, sizeof(double) * (size_t)nk * nk, s));
+    {
+        KLaunch k(c, P_NORM);
+        dim3 grid((nk + 127) / 128, nk);
+        k_dense_out<<<grid, 128, 0, s>>>(a->d_M, a->n, a->d_blk, a->d_op, a->d_val, a->nblk,
+                                         gap_free ? a->d_kept : nullptr, nk, d_out);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)nk * nk, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    NLF_CUDA(cudaFreeAsync(d_out, s));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_fetch_hcm(nlf_assembly *a, double *out)
+{
+    if (!a || !out) return fail(NLF_ERR_ARG, "nlf_assembly_fetch_hcm: NULL argument");
+    return dense_out(a, false, out);
+}
+
+NLF_EXPORT int nlf_assembly_fetch_gap_free(nlf_assembly *a, double *out)
+{
+    if (!a || !out) return fail(NLF_ERR_ARG, "nlf_assembly_fetch_gap_free: NULL argument");
+    return dense_out(a, true, out);
+}
+
+// used by nlf_batch_add_assembly (score.cu): the gap-free band never leaves the device
+int nlf_assembly_export_band(nlf_assembly *a, int bw, int pitch, double **d_band, int *n_out)
+{
+    nlf_ctx *c = a->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_gaps(a);
+    if (rc) return rc;
+    const int nk = (int)a->kept.size();
+    double *band;
+    NLF_CUDA(cudaMallocAsync(&band, sizeof(double) * (size_t)nk * pitch, c->stream));
+    {
+        KLaunch k(c, P_BANDIFY);
+        dim3 grid((pitch + 127) / 128, nk);
+        k_gap_band<<<grid, 128, 0, c->stream>>>(a->d_M, a->n, a->d_blk, a->d_op, a->d_val, a->nblk, a->d_kept, nk, bw,
+                                                pitch, band);
+    }
+    NLF_CUDA(cudaGetLastError());
+    *d_band = band;
+    *n_out = nk;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_destroy(nlf_assembly *a)
+{
+    if (!a) return NLF_OK;
+    cudaSetDevice(a->ctx->device);
+    cudaStream_t s = a->ctx->stream;
+    cudaFreeAsync(a->d_M, s); cudaFreeAsync(a->d_bias, s); cudaFreeAsync(a->d_blk, s);
+    cudaFreeAsync(a->d_op, s); cudaFreeAsync(a->d_val, s); cudaFreeAsync(a->d_kept, s);
+    delete a;
+    return NLF_OK;
+}

@@ -1,0 +1,1436 @@
+// score.cu -- scoring path of neoloop-caller on B200 (sm_100a):
+//   K1 bandify        dense gap-free matrix -> finite band        (callers.py:527-535)
+//   K5 diag means + isotonic expected + candidate gate             (callers.py:540-570)
+//   K7 window gates, O/E, gaussian, min-max -> float32 features    (callers.py:583-612, util.py:470-524)
+//   K8 random-forest traversal, ordered fp64 vote                  (callers.py:622)
+//   K9 threshold + compaction of the Donuts                        (callers.py:623-628)
+// All floating-point arithmetic that reaches a result is IEEE fp64 with explicit round-to-nearest
+// intrinsics (no FMA contraction; the file is also compiled with -fmad=false), in the exact
+// operation order of numpy / scipy.ndimage / sklearn as restated in oracle/c/nlf_oracle.c.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nlf {
+thread_local char g_err[512] = "";
+}
+using namespace nlf;
+
+// ---------------------------------------------------------------------------------------------
+// data layout in HBM (per job = one gap-free matrix of n bins)
+//   band  [n][pitch]  fp64   band[r][d] = G[r, r+d] for 0 <= d < upper+14, finite, else 0
+//   prob  [n][ndp]    fp64   prob[x][d-dlo] = forest probability of pixel (x, x+d); NaN = not scored
+//   slot  [n][ndp]    int32  feature slot (group*32+lane) of a scored pixel, -1 otherwise (optional)
+//   e     [upper+1]   fp64   isotonic expected of Peakachu.get_candidates
+// feature groups (shared by all jobs of a chunk)
+//   featT [group][F][32] fp32  features of up to 32 pixels of one matrix row, feature-major so
+//                              that the forest kernel's per-lane column is bank-conflict free
+//   hdr   [group]              {job, x, d0, lane mask}
+// ---------------------------------------------------------------------------------------------
+struct JobDev {
+    const double *band;
+    double *prob;
+    int *slot;
+    double *means;      // [upper+1] diagonal means (NaN where the diagonal is too short)
+    double *e;          // [upper+1]
+    double *pava_w;     // [upper+2] scratch
+    long long *pava_r;  // [upper+2] scratch
+    int *status;        // [0] error code of the job (0 ok)
+    unsigned long long *counts;  // [0] candidates, [1] scored, [2] donuts
+    int *don_i, *don_j;           // Donut outputs (capacity don_cap)
+    double *don_p, *don_v;
+    long long don_cap;
+    int n;
+    int ntx;            // number of x tiles
+};
+
+struct GroupHdr {
+    int job, x, d0;
+    unsigned mask;
+};
+
+__constant__ double c_gw[16];   // gaussian weights, radius 4: c_gw[0..8]
+
+// =============================================================================================
+// K1 bandify
+// =============================================================================================
+__global__ void k_bandify(const double *__restrict__ G, int n, int bw, int pitch, double *__restrict__ band,
+                          int *__restrict__ status)
+{
+    int r = blockIdx.y;
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= pitch) return;
+    double v = 0.0;
+    if (d < bw && r + d < n) {
+        v = G[(size_t)r * n + r + d];
+        if (!isfinite(v)) v = 0.0;
+    }
+    band[(size_t)r * pitch + d] = v;
+    // Peakachu keeps 13 sub-diagonals too (C-R > -14); the path feeds np.triu matrices, so any
+    // finite non-zero there means the caller broke the contract: report instead of mis-scoring.
+    if (d >= 1 && d < 14 && r - d >= 0) {
+        double u = G[(size_t)r * n + r - d];
+        if (u != 0.0 && isfinite(u)) atomicExch(status, NLF_ERR_LOWER_TRI);
+    }
+}
+
+// band given by the host with its own pitch -> canonical pitch, finite filter
+__global__ void k_band_copy(const double *__restrict__ src, int n, int src_pitch, int bw, int pitch,
+                            double *__restrict__ band)
+{
+    int r = blockIdx.y;
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= pitch) return;
+    double v = 0.0;
+    if (d < bw && d < src_pitch && r + d < n) {
+        v = src[(size_t)r * src_pitch + d];
+        if (!isfinite(v)) v = 0.0;
+    }
+    band[(size_t)r * pitch + d] = v;
+}
+
+// =============================================================================================
+// K5a per-diagonal means (numpy pairwise order): one thread per (job, diagonal); consecutive
+// threads read consecutive addresses of a band row.
+// =============================================================================================
+__global__ void k_diag_means(const JobDev *__restrict__ jobs, int lower, int upper, int pitch)
+{
+    const JobDev J = jobs[blockIdx.y];
+    int d = lower + blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > upper) return;
+    int len = J.n - d;
+    double m = __longlong_as_double(0x7ff8000000000000LL);
+    if (len > 5) {
+        const double *base = J.band + d;
+        size_t p = (size_t)pitch;
+        double s = np_pairwise_sum([=](int i) { return base[(size_t)i * p]; }, len);
+        m = __ddiv_rn(s, (double)len);
+    }
+    J.means[d] = m;
+}
+
+// K5b isotonic (decreasing) fit of the means: scipy's PAVA (pava_pybind.cpp) on the reversed
+// sequence, one thread per job (<= upper-lower+1 points).  e[d] = fit[min(d, last)].
+__global__ void k_isotonic(const JobDev *__restrict__ jobs, int lower, int upper)
+{
+    if (threadIdx.x != 0) return;
+    const JobDev J = jobs[blockIdx.x];
+    int last = min(upper, J.n - 6);          // diagonals lower..last have more than 5 entries
+    long long m = (long long)last - lower + 1;
+    if (m <= 0) { atomicExch(J.status, NLF_ERR_EMPTY_FIT); return; }
+    double *x = J.e;                         // reuse e[0..m) as the PAVA work array
+    double *w = J.pava_w;
+    long long *r = J.pava_r;
+    for (long long i = 0; i < m; i++) { x[i] = J.means[last - i]; w[i] = 1.0; }   // reversed
+    if (m > 1) {
+        r[0] = 0; r[1] = 1;
+        long long b = 0;
+        double xb_prev = x[0], wb_prev = w[0];
+        for (long long i = 1; i < m; ++i) {
+            b++;
+            double xb = x[i], wb = w[i], sb = 0;
+            if (xb_prev >= xb) {
+                b--;
+                sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
+                wb = __dadd_rn(wb, wb_prev);
+                xb = __ddiv_rn(sb, wb);
+                while (i < m - 1 && xb >= x[i + 1]) {
+                    i++;
+                    sb = __dadd_rn(sb, __dmul_rn(w[i], x[i]));
+                    wb = __dadd_rn(wb, w[i]);
+                    xb = __ddiv_rn(sb, wb);
+                }
+                while (b > 0 && x[b - 1] >= xb) {
+                    b--;
+                    sb = __dadd_rn(sb, __dmul_rn(w[b], x[b]));
+                    wb = __dadd_rn(wb, w[b]);
+                    xb = __ddiv_rn(sb, wb);
+                }
+            }
+            x[b] = xb_prev = xb;
+            w[b] = wb_prev = wb;
+            r[b + 1] = i + 1;
+        }
+        long long f = m - 1;
+        for (long long k = b; k >= 0; --k) {
+            long long t = r[k];
+            double xk = x[k];
+            for (long long i = f; i >= t; --i) x[i] = xk;
+            f = t - 1;
+        }
+    }
+    // un-reverse into w (scratch), then publish e[d] with out_of_bounds='clip'
+    for (long long i = 0; i < m; i++) w[i] = x[m - 1 - i];
+    for (int d = upper; d >= 0; d--) {
+        double v = __longlong_as_double(0x7ff8000000000000LL);
+        if (d >= lower) {
+            long long k = d - lower;
+            if (k > m - 1) k = m - 1;
+            v = w[k];
+        }
+        J.e[d] = v;
+    }
+}
+
+// =============================================================================================
+// K7 feature kernel.
+// Block = S warps (S = 2W+1); tile = TX matrix rows x 32 consecutive diagonals.  Warp a owns
+// window row a, lane l owns diagonal d0+l, so every shared-memory access of a warp is a run of
+// consecutive 8-byte words (conflict free) and no lane diverges inside the arithmetic.
+//   phase 0  band tile (+halo) -> smem raw R and observed/expected E = R / exp[|col-row|]
+//   phase 1  gates per pixel: candidate test, count_nonzero, lower-left mean (numpy order)
+//   phase 2  per matrix row x: axis-0 gaussian pass shared by the 32 windows of the row,
+//            then per window row the axis-1 pass, min/max, normalise, cast to float32.
+// =============================================================================================
+template <int W>
+struct FeatCfg {
+    static constexpr int S = 2 * W + 1;
+    static constexpr int F = S * S;
+    static constexpr int TX = 16;
+    static constexpr int TR = TX + 2 * W;       // tile rows incl. halo
+    static constexpr int TC = 32 + 4 * W;       // tile band columns incl. halo
+    static constexpr int VC = 32 + 2 * W;       // columns of the axis-0 result
+    static constexpr int NT = 32 * S;
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n)
+{
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+}
+
+template <int W>
+__global__ void __launch_bounds__(FeatCfg<W>::NT, 1)
+k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int lower, int upper,
+           int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, GroupHdr *__restrict__ hdr,
+           float *__restrict__ featT, unsigned *__restrict__ group_counter, unsigned max_groups,
+           int *__restrict__ overflow)
+{
+    using C = FeatCfg<W>;
+    constexpr int S = C::S, F = C::F, TX = C::TX, TR = C::TR, TC = C::TC, VC = C::VC, NT = C::NT;
+    __shared__ double Rt[TR][TC];
+    __shared__ double Et[TR][TC];
+    __shared__ unsigned char Hs[TR][TC];
+    __shared__ double Vx[S][VC];
+    __shared__ double red_min[S][32];
+    __shared__ double red_max[S][32];
+    __shared__ unsigned passmask[TX];
+    __shared__ unsigned s_group_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- tile -> (job, x0, d0)
+    int t = blockIdx.x;
+    int lo = 0, hi = njobs;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_base[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int job = lo;
+    const JobDev J = jobs[job];
+    if (*J.status != 0) return;
+    const int lt = t - tile_base[job];
+    const int dlo = max(lower, W + 2);
+    const int x0 = (lt / ndt) * TX;
+    const int d0 = dlo + (lt % ndt) * 32;
+    const int n = J.n;
+    const int bw = upper + 14;
+
+    // ---- phase 0: load tile
+    for (int k = tid; k < TR * TC; k += NT) {
+        int rr = k / TC, cc = k % TC;
+        int r = x0 - W + rr;
+        int dd = d0 - 2 * W + cc;
+        double v = 0.0;
+        if (r >= 0 && r < n && dd >= 0 && dd < bw) v = J.band[(size_t)r * pitch + dd];
+        Rt[rr][cc] = v;
+        int ad = dd < 0 ? -dd : dd;
+        Et[rr][cc] = (ad < nexp) ? __ddiv_rn(v, expv[ad]) : v;
+    }
+    __syncthreads();
+    for (int k = tid; k < TR * TC; k += NT) {
+        int rr = k / TC, cc = k % TC;
+        int c = 0;
+        if (cc + 2 * W < TC) {
+#pragma unroll
+            for (int b = 0; b < S; b++) c += (Rt[rr][cc + b] != 0.0);
+        }
+        Hs[rr][cc] = (unsigned char)c;
+    }
+    __syncthreads();
+
+    // ---- phase 1: gates; warp handles tile row xi, lane = diagonal
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int xi = warp; xi < TX; xi += S) {
+        int x = x0 + xi, d = d0 + lane, y = x + d;
+        bool in_band = (x < n) && (d <= upper);
+        bool ok = in_band && (x - W >= 0) && (y + W + 1 <= n) && (n - d > 1);
+        if (ok) {
+            double e = J.e[d];
+            double v = Rt[xi + W][lane + 2 * W];
+            ok = (e > 0) && (__ddiv_rn(v, e) > 0);
+        }
+        if (ok) {
+            int nz = 0;
+#pragma unroll
+            for (int a = 0; a < S; a++) nz += Hs[xi + a][lane + 2 * W - a];
+            ok = !((double)nz < (double)F * 0.1);
+        }
+        if (ok) {
+            // window[:w,:w].mean(): numpy pairwise order over the C-flattened w x w block
+            auto ld = [&](int k) { int a = k / W, b = k % W; return Rt[xi + a][lane + 2 * W + b - a]; };
+            double ll = __ddiv_rn(np_leaf_sum(ld, 0, W * W), (double)(W * W));
+            ok = (ll > 0);
+            if (ok) ok = (__ddiv_rn(Rt[xi + W][lane + 2 * W], ll) > 0.1);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) passmask[xi] = m;
+        if (in_band) {
+            size_t o = (size_t)x * ndp + (d - dlo);
+            J.prob[o] = qnan;
+            if (J.slot) J.slot[o] = -1;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cnt = 0;
+        for (int xi = 0; xi < TX; xi++) cnt += (passmask[xi] != 0);
+        unsigned base = cnt ? atomicAdd(group_counter, (unsigned)cnt) : 0u;
+        if (cnt && base + cnt > max_groups) { atomicExch(overflow, 1); base = 0xffffffffu; }
+        s_group_base = base;
+    }
+    __syncthreads();
+    unsigned gbase = s_group_base;
+    if (gbase == 0xffffffffu) return;
+
+    // lanes whose window reaches beyond the expected table stay un-normalised (util.py:480-481)
+    unsigned raw_lanes = 0;
+    {
+        bool raw = (d0 + lane + 2 * W) >= nexp;
+        raw_lanes = __ballot_sync(0xffffffffu, raw);
+    }
+
+    // ---- phase 2: rows
+    unsigned g = gbase;
+    for (int xi = 0; xi < TX; xi++) {
+        unsigned pm = passmask[xi];
+        if (!pm) continue;
+        const int x = x0 + xi;
+        if (tid == 0) { GroupHdr h; h.job = job; h.x = x; h.d0 = d0; h.mask = pm; hdr[g] = h; }
+        float *fdst = featT + (size_t)g * F * 32;
+#pragma unroll 1
+        for (int mode = 0; mode < 2; mode++) {
+            unsigned mm = mode ? (pm & raw_lanes) : (pm & ~raw_lanes);
+            if (!mm) continue;
+            const double (*T)[TC] = mode ? Rt : Et;
+            // stage A: axis-0 pass, warp a -> Vx[a][*]
+            {
+                const int a = warp;
+                int ra[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) ra[k] = reflect_idx(a + k - 4, S);
+                for (int cc = lane; cc < VC; cc += 32) {
+                    // src(a', cc) = T[xi + a'][cc - a' + 2W]
+                    double v = __dmul_rn(T[xi + ra[4]][cc - ra[4] + 2 * W], c_gw[4]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        double l = T[xi + ra[j]][cc - ra[j] + 2 * W];
+                        double r = T[xi + ra[8 - j]][cc - ra[8 - j] + 2 * W];
+                        v = __dadd_rn(v, __dmul_rn(__dadd_rn(l, r), c_gw[j]));
+                    }
+                    Vx[a][cc] = v;
+                }
+            }
+            __syncthreads();
+            // stage B: axis-1 pass for window row a = warp, window of lane
+            double in[S], out[S];
+#pragma unroll
+            for (int b = 0; b < S; b++) in[b] = Vx[warp][lane + b];
+            double rmin, rmax;
+            bool has_nan = false;
+#pragma unroll
+            for (int b = 0; b < S; b++) {
+                double v = __dmul_rn(in[b], c_gw[4]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // pair (b-4+j, b+4-j), outermost first
+                    const int il = (b - 4 + j) < 0 ? -(b - 4 + j) - 1 : (b - 4 + j);
+                    const int ir = (b + 4 - j) >= S ? 2 * S - 1 - (b + 4 - j) : (b + 4 - j);
+                    v = __dadd_rn(v, __dmul_rn(__dadd_rn(in[il], in[ir]), c_gw[j]));
+                }
+                out[b] = v;
+                has_nan |= (v != v);
+                if (b == 0) { rmin = v; rmax = v; }
+                else { rmin = (v < rmin) ? v : rmin; rmax = (v > rmax) ? v : rmax; }
+            }
+            if (has_nan) { rmin = qnan; rmax = qnan; }
+            red_min[warp][lane] = rmin;
+            red_max[warp][lane] = rmax;
+            __syncthreads();
+            double mn = red_min[0][lane], mx = red_max[0][lane];
+            bool nn = (mn != mn);
+#pragma unroll
+            for (int a = 1; a < S; a++) {
+                double u = red_min[a][lane], v = red_max[a][lane];
+                nn |= (u != u);
+                mn = (u < mn) ? u : mn;
+                mx = (v > mx) ? v : mx;
+            }
+            if (nn) { mn = qnan; mx = qnan; }
+            if ((mm >> lane) & 1u) {
+                double den = __dsub_rn(mx, mn);
+#pragma unroll
+                for (int b = 0; b < S; b++) {
+                    double f = __ddiv_rn(__dsub_rn(out[b], mn), den);
+                    fdst[(size_t)(warp * S + b) * 32 + lane] = __double2float_rn(f);
+                }
+            }
+            // red_* are rewritten only after the next stage-A barrier; Vx only after this point
+            __syncthreads();
+        }
+        if (warp == 0 && ((pm >> lane) & 1u)) {
+            if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)(g * 32u + lane);
+        }
+        g++;
+    }
+}
+
+// =============================================================================================
+// K8 forest.  One warp per feature group, lane = pixel.  Every lane walks all trees in
+// estimator order and adds the class-1 leaf fractions sequentially in fp64 (the order in which
+// sklearn accumulates, _forest.py:704-717), then divides by the number of trees.
+// Node = 8 bytes {float thr (largest float <= sklearn's float64 threshold), u32 packed}:
+//   packed bits 0-7 feature (255 = leaf), bit 8 missing_go_to_left, bits 9-31 right child.
+// The left child of node k is k+1 (sklearn grows trees depth-first).
+// =============================================================================================
+struct ForestDev {
+    const uint2 *nodes;       // all trees concatenated
+    const double *leaf;       // class-1 fraction per node (only read at leaves)
+    const int *tree_off;      // [T+1]
+    int n_trees;
+    int n_features;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict__ featT,
+         const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp)
+{
+    extern __shared__ float fs[];     // [WARPS][F][32]
+    const int F = fr.n_features;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *my = fs + (size_t)warp * F * 32;
+    const unsigned ngroups = *group_counter;
+    const int dlo = max(lower, W + 2);
+    const int T = fr.n_trees;
+    for (unsigned g = blockIdx.x * WARPS + warp; g < ngroups; g += gridDim.x * WARPS) {
+        const float4 *src = reinterpret_cast<const float4 *>(featT + (size_t)g * F * 32);
+        float4 *dst = reinterpret_cast<float4 *>(my);
+        for (int k = lane; k < F * 8; k += 32) dst[k] = src[k];
+        __syncwarp();
+        const GroupHdr h = hdr[g];
+        if ((h.mask >> lane) & 1u) {
+            double acc = 0.0;
+            int t = 0;
+            int base = fr.tree_off[0];
+            int node = 0;
+            while (t < T) {
+                uint2 nd = __ldg(&fr.nodes[base + node]);
+                unsigned f = nd.y & 0xffu;
+                if (f == 0xffu) {
+                    acc = __dadd_rn(acc, __ldg(&fr.leaf[base + node]));
+                    t++;
+                    node = 0;
+                    if (t < T) base = fr.tree_off[t];
+                } else {
+                    float xv = my[f * 32 + lane];
+                    float thr = __uint_as_float(nd.x);
+                    bool left = (xv != xv) ? ((nd.y >> 8) & 1u) : (xv <= thr);
+                    node = left ? node + 1 : (int)(nd.y >> 9);
+                }
+            }
+            double p = __ddiv_rn(acc, (double)T);
+            const JobDev J = jobs[h.job];
+            J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = p;
+        }
+        __syncwarp();
+    }
+}
+
+// forest on plain row-major float32 rows (nlf_forest_predict): thread per row
+__global__ void k_forest_rows(ForestDev fr, const float *__restrict__ X, long long N, double *__restrict__ out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float *x = X + (size_t)i * fr.n_features;
+    double acc = 0.0;
+    for (int t = 0; t < fr.n_trees; t++) {
+        int base = fr.tree_off[t], node = 0;
+        while (true) {
+            uint2 nd = __ldg(&fr.nodes[base + node]);
+            unsigned f = nd.y & 0xffu;
+            if (f == 0xffu) break;
+            float xv = x[f];
+            bool left = (xv != xv) ? ((nd.y >> 8) & 1u) : (xv <= __uint_as_float(nd.x));
+            node = left ? node + 1 : (int)(nd.y >> 9);
+        }
+        acc = __dadd_rn(acc, fr.leaf[base + node]);
+    }
+    out[i] = __ddiv_rn(acc, (double)fr.n_trees);
+}
+
+// =============================================================================================
+// K9 threshold: count scored pixels, append pixels with proba >= thre (callers.py:625-628)
+// with their contact value M[i,j].  Also counts the candidates of get_candidates.
+// =============================================================================================
+__global__ void k_threshold(const JobDev *__restrict__ jobs, int lower, int upper, int W, int pitch, int ndp,
+                            double thre)
+{
+    const JobDev J = jobs[blockIdx.y];
+    if (*J.status != 0) return;
+    const int dlo = max(lower, W + 2);
+    const int nd = upper - dlo + 1;
+    const long long total = (long long)J.n * nd;
+    unsigned long long scored = 0, donuts = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+         k += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(k / nd), dd = (int)(k % nd);
+        double p = J.prob[(size_t)x * ndp + dd];
+        if (p == p) {
+            scored++;
+            if (p >= thre) {
+                donuts++;
+                unsigned long long pos = atomicAdd(&J.counts[3], 1ULL);
+                if ((long long)pos < J.don_cap) {
+                    int d = dlo + dd;
+                    J.don_i[pos] = x;
+                    J.don_j[pos] = x + d;
+                    J.don_p[pos] = p;
+                    J.don_v[pos] = J.band[(size_t)x * pitch + d];
+                }
+            }
+        }
+    }
+    // warp reduce the counters
+    for (int o = 16; o; o >>= 1) {
+        scored += __shfl_down_sync(0xffffffffu, scored, o);
+        donuts += __shfl_down_sync(0xffffffffu, donuts, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (scored) atomicAdd(&J.counts[1], scored);
+        if (donuts) atomicAdd(&J.counts[2], donuts);
+    }
+}
+
+// candidates of Peakachu.get_candidates: all (x, d), lower <= d <= upper, n-d > 1, e[d] > 0,
+// band/e > 0.  flag = 1 -> count only; also used for ordered compaction below.
+__device__ __forceinline__ bool is_candidate(const JobDev &J, int x, int d, int pitch)
+{
+    if (x + d >= J.n || J.n - d <= 1) return false;
+    double e = J.e[d];
+    if (!(e > 0)) return false;
+    return __ddiv_rn(J.band[(size_t)x * pitch + d], e) > 0;
+}
+
+__global__ void k_count_candidates(const JobDev *__restrict__ jobs, int lower, int upper, int pitch)
+{
+    const JobDev J = jobs[blockIdx.y];
+    if (*J.status != 0) return;
+    const int nd = upper - lower + 1;
+    const long long total = (long long)J.n * nd;
+    unsigned long long c = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+         k += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(k / nd), d = lower + (int)(k % nd);
+        c += is_candidate(J, x, d, pitch);
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&J.counts[0], c);
+}
+
+// Ordered (diagonal-major, row-ascending) listing used by the API/test accessors.
+// mode 0: candidates; mode 1: scored pixels (prob not NaN).  One block per diagonal:
+// pass A counts, pass B (after an exclusive scan of the counts) writes.
+__global__ void k_diag_count(JobDev J, int mode, int lower, int upper, int W, int pitch, int ndp, int *cnt)
+{
+    int d = lower + blockIdx.x;
+    const int dlo = max(lower, W + 2);
+    int c = 0;
+    for (int x = threadIdx.x; x + d < J.n; x += blockDim.x) {
+        bool f;
+        if (mode == 0) f = is_candidate(J, x, d, pitch);
+        else { f = false; if (d >= dlo) { double p = J.prob[(size_t)x * ndp + (d - dlo)]; f = (p == p); } }
+        c += f;
+    }
+    __shared__ int sh[32];
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) s += sh[k];
+        cnt[blockIdx.x] = s;
+    }
+}
+
+__global__ void k_diag_fill(JobDev J, int mode, int lower, int upper, int W, int pitch, int ndp,
+                            const long long *__restrict__ off, int *oi, int *oj, double *op, int *oslot)
+{
+    int d = lower + blockIdx.x;
+    const int dlo = max(lower, W + 2);
+    __shared__ int wsum[32];
+    __shared__ long long s_base;
+    if (threadIdx.x == 0) s_base = off[blockIdx.x];
+    __syncthreads();
+    const int nw = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int x0 = 0; x0 + d < J.n; x0 += blockDim.x) {
+        int x = x0 + threadIdx.x;
+        bool f = false;
+        double p = 0;
+        if (x + d < J.n) {
+            if (mode == 0) f = is_candidate(J, x, d, pitch);
+            else if (d >= dlo) { p = J.prob[(size_t)x * ndp + (d - dlo)]; f = (p == p); }
+        }
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int k = 0; k < nw; k++) { if (k < warp) before += wsum[k]; tot += wsum[k]; }
+        if (f) {
+            long long pos = s_base + before + __popc(b & ((1u << lane) - 1u));
+            oi[pos] = x;
+            oj[pos] = x + d;
+            if (op) op[pos] = p;
+            if (oslot) oslot[pos] = J.slot ? J.slot[(size_t)x * ndp + (d - dlo)] : -1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void k_gather_features(const float *__restrict__ featT, const int *__restrict__ slots, long long N, int F,
+                                  float *__restrict__ out)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N * F) return;
+    long long row = k / F;
+    int f = (int)(k % F);
+    int s = slots[row];
+    out[k] = featT[((size_t)(s >> 5) * F + f) * 32 + (s & 31)];
+}
+
+// =============================================================================================
+// Peakachu.getwindow for arbitrary coordinates, float64 output (API / test accessor; the hot
+// path is k_features).  One warp per coordinate, same arithmetic, order-preserving compaction is
+// done by the host wrapper from the per-coordinate pass flags.
+// =============================================================================================
+template <int W>
+__global__ void k_getwindow(JobDev J, int upper, int pitch, const int *__restrict__ xi, const int *__restrict__ yi,
+                            long long nc, const double *__restrict__ expv, int nexp, unsigned char *__restrict__ pass,
+                            double *__restrict__ fea)
+{
+    constexpr int S = 2 * W + 1, F = S * S;
+    __shared__ double win[4][F], tmp[4][F], red[4][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long k = (long long)blockIdx.x * 4 + warp;
+    if (k >= nc) return;
+    const int x = xi[k], y = yi[k], n = J.n, bw = upper + 14;
+    bool ok = (x - W >= 0) && (y + W + 1 <= n) && (y - x - 2 >= W);
+    if (!ok) { if (lane == 0) pass[k] = 0; return; }
+    int nz = 0;
+    for (int c = lane; c < F; c += 32) {
+        int a = c / S, b = c % S;
+        int r = x - W + a, cc = y - W + b, d = cc - r;
+        double v = 0.0;
+        if (d >= 0 && d < bw) v = J.band[(size_t)r * pitch + d];
+        win[warp][c] = v;
+        nz += (v != 0.0);
+    }
+    for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    __syncwarp();
+    ok = !((double)nz < (double)F * 0.1);
+    if (ok) {
+        auto ld = [&](int q) { return win[warp][(q / W) * S + (q % W)]; };
+        double ll = __ddiv_rn(np_leaf_sum(ld, 0, W * W), (double)(W * W));
+        ok = (ll > 0) && (__ddiv_rn(win[warp][W * S + W], ll) > 0.1);
+    }
+    if (!ok) { if (lane == 0) pass[k] = 0; return; }
+    const bool norm = (y - x + 2 * W) < nexp;
+    if (norm)
+        for (int c = lane; c < F; c += 32) {
+            int a = c / S, b = c % S;
+            int d = (y - W + b) - (x - W + a);
+            win[warp][c] = __ddiv_rn(win[warp][c], expv[d < 0 ? -d : d]);
+        }
+    __syncwarp();
+    for (int c = lane; c < F; c += 32) {
+        int a = c / S, b = c % S;
+        double v = __dmul_rn(win[warp][a * S + b], c_gw[4]);
+        for (int j = 0; j < 4; j++) {
+            double l = win[warp][reflect_idx(a - 4 + j, S) * S + b], r = win[warp][reflect_idx(a + 4 - j, S) * S + b];
+            v = __dadd_rn(v, __dmul_rn(__dadd_rn(l, r), c_gw[j]));
+        }
+        tmp[warp][c] = v;
+    }
+    __syncwarp();
+    double mn = 0, mx = 0;
+    bool first = true, nn = false;
+    for (int c = lane; c < F; c += 32) {
+        int a = c / S, b = c % S;
+        double v = __dmul_rn(tmp[warp][a * S + b], c_gw[4]);
+        for (int j = 0; j < 4; j++) {
+            double l = tmp[warp][a * S + reflect_idx(b - 4 + j, S)], r = tmp[warp][a * S + reflect_idx(b + 4 - j, S)];
+            v = __dadd_rn(v, __dmul_rn(__dadd_rn(l, r), c_gw[j]));
+        }
+        win[warp][c] = v;       // safe: each lane only rewrites cells it alone reads from now on
+        nn |= (v != v);
+        if (first) { mn = mx = v; first = false; }
+        else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+    }
+    red[warp][lane] = mn; red[warp][32 + lane] = mx;
+    unsigned anynan = __ballot_sync(0xffffffffu, nn);
+    __syncwarp();
+    for (int l = 0; l < 32; l++) {
+        double u = red[warp][l], v = red[warp][32 + l];
+        mn = u < mn ? u : mn; mx = v > mx ? v : mx;
+    }
+    if (anynan) { mn = mx = __longlong_as_double(0x7ff8000000000000LL); }
+    double den = __dsub_rn(mx, mn);
+    for (int c = lane; c < F; c += 32) fea[(size_t)k * F + c] = __ddiv_rn(__dsub_rn(win[warp][c], mn), den);
+    if (lane == 0) pass[k] = 1;
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct nlf_forest {
+    nlf_ctx *ctx;
+    ForestDev dev;
+    uint2 *d_nodes = nullptr;
+    double *d_leaf = nullptr;
+    int *d_off = nullptr;
+    long long n_nodes = 0;
+};
+
+struct HostJob {
+    int n = 0;
+    double *d_dense = nullptr;   // freed after bandify
+    double *d_band = nullptr;
+    bool band_owned = true;
+    double *d_prob = nullptr;
+    int *d_slot = nullptr;
+    double *d_means = nullptr, *d_e = nullptr, *d_pw = nullptr;
+    long long *d_pr = nullptr;
+    int *d_status = nullptr;
+    unsigned long long *d_counts = nullptr;
+    int *d_don_i = nullptr, *d_don_j = nullptr;
+    double *d_don_p = nullptr, *d_don_v = nullptr;
+    long long don_cap = 0;
+    unsigned long long counts[4] = {0, 0, 0, 0};
+    int status = 0;
+};
+
+struct nlf_batch {
+    nlf_ctx *ctx = nullptr;
+    int lower = 4, upper = 400, pitch = 416, bw = 414;
+    int W = 0, ndp = 0, ndt = 0;
+    bool keep_slots = false;
+    std::vector<HostJob> jobs;
+    JobDev *d_jobs = nullptr;
+    int *d_tile_base = nullptr;
+    GroupHdr *d_hdr = nullptr;
+    float *d_featT = nullptr;
+    unsigned *d_group_counter = nullptr;
+    int *d_overflow = nullptr;
+    double *d_exp = nullptr;
+    unsigned max_groups = 0;
+    int total_tiles = 0;
+    long long total_groups = 0;
+    bool prepared = false, scored = false, counted = false;
+};
+
+extern int nlf_assembly_export_band(nlf_assembly *a, int bw, int pitch, double **d_band, int *n_out);
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+NLF_EXPORT int nlf_version(void) { return 100; }
+NLF_EXPORT const char *nlf_last_error(void) { return g_err; }
+
+NLF_EXPORT int nlf_device_count(int *count)
+{
+    NLF_CUDA(cudaGetDeviceCount(count));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_ctx_create(int device, nlf_ctx **out)
+{
+    if (!out) return fail(NLF_ERR_ARG, "nlf_ctx_create: out is NULL");
+    int ndev = 0;
+    NLF_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(NLF_ERR_ARG, "device %d not in [0,%d)", device, ndev);
+    NLF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NLF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(NLF_ERR_CUDA, "device %d is sm_%d%d; libnlf_b200 is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    nlf_ctx *c = new nlf_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    NLF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    NLF_CUDA(cudaEventCreate(&c->t0));
+    NLF_CUDA(cudaEventCreate(&c->t1));
+    cudaMemPool_t pool;
+    NLF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    NLF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_ctx_destroy(nlf_ctx *c)
+{
+    if (!c) return NLF_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->prof_resolve();
+    for (auto e : c->free_events) cudaEventDestroy(e);
+    cudaEventDestroy(c->t0);
+    cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_ctx_sync(nlf_ctx *c)
+{
+    NLF_CUDA(cudaSetDevice(c->device));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_timer_start(nlf_ctx *c)
+{
+    NLF_CUDA(cudaSetDevice(c->device));
+    NLF_CUDA(cudaEventRecord(c->t0, c->stream));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_timer_stop(nlf_ctx *c, float *ms)
+{
+    NLF_CUDA(cudaSetDevice(c->device));
+    NLF_CUDA(cudaEventRecord(c->t1, c->stream));
+    NLF_CUDA(cudaEventSynchronize(c->t1));
+    NLF_CUDA(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_launch_count(nlf_ctx *c, long long *count) { *count = c->launches; return NLF_OK; }
+NLF_EXPORT int nlf_profile_enable(nlf_ctx *c, int on) { c->profile = on != 0; return NLF_OK; }
+NLF_EXPORT int nlf_profile_reset(nlf_ctx *c)
+{
+    c->prof_resolve();
+    for (int i = 0; i < P_NCLASS; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return NLF_OK;
+}
+NLF_EXPORT int nlf_profile_read(nlf_ctx *c, int which, float *total_ms, long long *launches)
+{
+    if (which < 0 || which >= P_NCLASS) return fail(NLF_ERR_ARG, "profile class %d", which);
+    NLF_CUDA(cudaSetDevice(c->device));
+    c->prof_resolve();
+    *total_ms = c->prof_ms[which];
+    *launches = c->prof_n[which];
+    return NLF_OK;
+}
+
+// ---- forest -----------------------------------------------------------------------------------
+NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_off, const int32_t *left,
+                                 const int32_t *right, const int32_t *feature, const double *threshold,
+                                 const uint8_t *missing_left, const double *leaf_p1, int n_features,
+                                 nlf_forest **out)
+{
+    if (!ctx || !out || n_trees <= 0) return fail(NLF_ERR_ARG, "nlf_forest_create: bad arguments");
+    if (n_features <= 0 || n_features >= 255)
+        return fail(NLF_ERR_ARG, "n_features=%d not supported (node format holds 1..254)", n_features);
+    long long total = tree_off[n_trees];
+    std::vector<uint2> nodes((size_t)total);
+    std::vector<int> off(n_trees + 1);
+    for (int t = 0; t <= n_trees; t++) off[t] = (int)tree_off[t];
+    for (int t = 0; t < n_trees; t++) {
+        long long b = tree_off[t], cnt = tree_off[t + 1] - b;
+        if (cnt >= (1 << 23)) return fail(NLF_ERR_ARG, "tree %d has %lld nodes (limit 2^23)", t, cnt);
+        for (long long k = 0; k < cnt; k++) {
+            uint2 nd;
+            if (left[b + k] < 0) {
+                nd.x = 0; nd.y = 0xffu;
+            } else {
+                if (left[b + k] != k + 1)
+                    return fail(NLF_ERR_ARG, "tree %d node %lld: left child %d is not node+1 (depth-first layout expected)",
+                                t, k, left[b + k]);
+                if (feature[b + k] < 0 || feature[b + k] >= n_features)
+                    return fail(NLF_ERR_ARG, "tree %d node %lld: feature %d out of range", t, k, feature[b + k]);
+                double th = threshold[b + k];
+                float tf = (float)th;
+                if ((double)tf > th) tf = nextafterf(tf, -INFINITY);   // largest float <= th
+                memcpy(&nd.x, &tf, 4);
+                nd.y = (unsigned)feature[b + k] | ((missing_left && missing_left[b + k]) ? 0x100u : 0u) |
+                       ((unsigned)right[b + k] << 9);
+            }
+            nodes[(size_t)(b + k)] = nd;
+        }
+    }
+    NLF_CUDA(cudaSetDevice(ctx->device));
+    nlf_forest *f = new nlf_forest();
+    f->ctx = ctx;
+    f->n_nodes = total;
+    NLF_CUDA(cudaMalloc(&f->d_nodes, sizeof(uint2) * (size_t)total));
+    NLF_CUDA(cudaMalloc(&f->d_leaf, sizeof(double) * (size_t)total));
+    NLF_CUDA(cudaMalloc(&f->d_off, sizeof(int) * (size_t)(n_trees + 1)));
+    NLF_CUDA(cudaMemcpy(f->d_nodes, nodes.data(), sizeof(uint2) * (size_t)total, cudaMemcpyHostToDevice));
+    NLF_CUDA(cudaMemcpy(f->d_leaf, leaf_p1, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice));
+    NLF_CUDA(cudaMemcpy(f->d_off, off.data(), sizeof(int) * (size_t)(n_trees + 1), cudaMemcpyHostToDevice));
+    f->dev.nodes = f->d_nodes;
+    f->dev.leaf = f->d_leaf;
+    f->dev.tree_off = f->d_off;
+    f->dev.n_trees = n_trees;
+    f->dev.n_features = n_features;
+    *out = f;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_forest_destroy(nlf_forest *f)
+{
+    if (!f) return NLF_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaFree(f->d_nodes);
+    cudaFree(f->d_leaf);
+    cudaFree(f->d_off);
+    delete f;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_forest_predict(nlf_forest *f, const float *X, long long N, double *proba)
+{
+    nlf_ctx *c = f->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    if (N <= 0) return NLF_OK;
+    float *dX;
+    double *dP;
+    size_t bytes = sizeof(float) * (size_t)N * f->dev.n_features;
+    NLF_CUDA(cudaMallocAsync(&dX, bytes, c->stream));
+    NLF_CUDA(cudaMallocAsync(&dP, sizeof(double) * (size_t)N, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(dX, X, bytes, cudaMemcpyHostToDevice, c->stream));
+    {
+        KLaunch k(c, P_FOREST);
+        k_forest_rows<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(f->dev, dX, N, dP);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaMemcpyAsync(proba, dP, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    NLF_CUDA(cudaFreeAsync(dX, c->stream));
+    NLF_CUDA(cudaFreeAsync(dP, c->stream));
+    return NLF_OK;
+}
+
+// ---- batch ------------------------------------------------------------------------------------
+NLF_EXPORT int nlf_batch_create(nlf_ctx *ctx, int lower, int upper, nlf_batch **out)
+{
+    if (!ctx || !out) return fail(NLF_ERR_ARG, "nlf_batch_create: NULL argument");
+    if (lower < 0 || upper < lower || upper > 4000) return fail(NLF_ERR_ARG, "bad band limits lower=%d upper=%d", lower, upper);
+    nlf_batch *b = new nlf_batch();
+    b->ctx = ctx;
+    b->lower = lower;
+    b->upper = upper;
+    b->bw = upper + 14;
+    b->pitch = round_up(b->bw, 4);
+    *out = b;
+    return NLF_OK;
+}
+
+static int alloc_job_common(nlf_batch *b, HostJob &j)
+{
+    nlf_ctx *c = b->ctx;
+    int up1 = b->upper + 2;
+    NLF_CUDA(cudaMallocAsync(&j.d_means, sizeof(double) * up1, c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_e, sizeof(double) * up1, c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_pw, sizeof(double) * up1, c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_pr, sizeof(long long) * up1, c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_status, sizeof(int), c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_counts, sizeof(unsigned long long) * 4, c->stream));
+    NLF_CUDA(cudaMemsetAsync(j.d_status, 0, sizeof(int), c->stream));
+    NLF_CUDA(cudaMemsetAsync(j.d_counts, 0, sizeof(unsigned long long) * 4, c->stream));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
+{
+    if (!b || !G || n <= 0) return fail(NLF_ERR_ARG, "nlf_batch_add_dense: bad arguments");
+    if (n > 65535) return fail(NLF_ERR_ARG, "dense input limited to n <= 65535 (use the band input), got %d", n);
+    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    HostJob j;
+    j.n = n;
+    int rc = alloc_job_common(b, j);
+    if (rc) return rc;
+    NLF_CUDA(cudaMallocAsync(&j.d_dense, sizeof(double) * (size_t)n * n, c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_band, sizeof(double) * (size_t)n * b->pitch, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(j.d_dense, G, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+    {
+        KLaunch k(c, P_BANDIFY);
+        dim3 grid((b->pitch + 127) / 128, n);
+        k_bandify<<<grid, 128, 0, c->stream>>>(j.d_dense, n, b->bw, b->pitch, j.d_band, j.d_status);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaFreeAsync(j.d_dense, c->stream));
+    j.d_dense = nullptr;
+    b->jobs.push_back(j);
+    return (int)b->jobs.size() - 1;
+}
+
+NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int pitch)
+{
+    if (!b || !band || n <= 0 || pitch <= 0) return fail(NLF_ERR_ARG, "nlf_batch_add_band: bad arguments");
+    if (n > 65535) return fail(NLF_ERR_ARG, "band input limited to n <= 65535 rows per job, got %d (shard the chromosome)", n);
+    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    HostJob j;
+    j.n = n;
+    int rc = alloc_job_common(b, j);
+    if (rc) return rc;
+    double *d_src;
+    NLF_CUDA(cudaMallocAsync(&d_src, sizeof(double) * (size_t)n * pitch, c->stream));
+    NLF_CUDA(cudaMallocAsync(&j.d_band, sizeof(double) * (size_t)n * b->pitch, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(d_src, band, sizeof(double) * (size_t)n * pitch, cudaMemcpyHostToDevice, c->stream));
+    {
+        KLaunch k(c, P_BANDIFY);
+        dim3 grid((b->pitch + 127) / 128, n);
+        k_band_copy<<<grid, 128, 0, c->stream>>>(d_src, n, pitch, b->bw, b->pitch, j.d_band);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaFreeAsync(d_src, c->stream));
+    b->jobs.push_back(j);
+    return (int)b->jobs.size() - 1;
+}
+
+NLF_EXPORT int nlf_batch_add_assembly(nlf_batch *b, nlf_assembly *a)
+{
+    if (!b || !a) return fail(NLF_ERR_ARG, "nlf_batch_add_assembly: NULL argument");
+    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    HostJob j;
+    int rc = nlf_assembly_export_band(a, b->bw, b->pitch, &j.d_band, &j.n);
+    if (rc) return rc;
+    rc = alloc_job_common(b, j);
+    if (rc) return rc;
+    b->jobs.push_back(j);
+    return (int)b->jobs.size() - 1;
+}
+
+NLF_EXPORT int nlf_batch_njobs(nlf_batch *b) { return b ? (int)b->jobs.size() : 0; }
+
+template <int W>
+static int launch_features(nlf_batch *b, int total_tiles, int nexp)
+{
+    nlf_ctx *c = b->ctx;
+    KLaunch k(c, P_FEATURE);
+    k_features<W><<<total_tiles, FeatCfg<W>::NT, 0, c->stream>>>(
+        b->d_jobs, b->d_tile_base, (int)b->jobs.size(), b->lower, b->upper, b->pitch, b->ndp, b->ndt, b->d_exp, nexp,
+        b->d_hdr, b->d_featT, b->d_group_counter, b->max_groups, b->d_overflow);
+    return NLF_OK;
+}
+
+// upload the per-job descriptors (pointers that are still NULL stay NULL)
+static int upload_jobs(nlf_batch *b, int w)
+{
+    nlf_ctx *c = b->ctx;
+    const int nj = (int)b->jobs.size();
+    const int TX = 16;
+    std::vector<JobDev> jd(nj);
+    std::vector<int> tb(nj + 1);
+    int tiles = 0;
+    long long groups = 0;
+    for (int k = 0; k < nj; k++) {
+        HostJob &j = b->jobs[k];
+        JobDev &d = jd[k];
+        d.band = j.d_band; d.prob = j.d_prob; d.slot = j.d_slot; d.means = j.d_means; d.e = j.d_e;
+        d.pava_w = j.d_pw; d.pava_r = j.d_pr; d.status = j.d_status; d.counts = j.d_counts;
+        d.don_i = j.d_don_i; d.don_j = j.d_don_j; d.don_p = j.d_don_p; d.don_v = j.d_don_v; d.don_cap = j.don_cap;
+        d.n = j.n;
+        d.ntx = (j.n + TX - 1) / TX;
+        tb[k] = tiles;
+        tiles += d.ntx * std::max(1, b->ndt);
+        groups += (long long)d.ntx * TX * std::max(1, b->ndt);
+    }
+    tb[nj] = tiles;
+    (void)w;
+    if (!b->d_jobs) {
+        NLF_CUDA(cudaMallocAsync(&b->d_jobs, sizeof(JobDev) * nj, c->stream));
+        NLF_CUDA(cudaMallocAsync(&b->d_tile_base, sizeof(int) * (nj + 1), c->stream));
+    }
+    // pageable sources: the copies are staged before these calls return
+    NLF_CUDA(cudaMemcpyAsync(b->d_jobs, jd.data(), sizeof(JobDev) * nj, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(b->d_tile_base, tb.data(), sizeof(int) * (nj + 1), cudaMemcpyHostToDevice, c->stream));
+    b->total_tiles = tiles;
+    b->total_groups = groups;
+    return NLF_OK;
+}
+
+// K5: diagonal means, isotonic expected, candidate count.  Independent of the model.
+static int batch_prepare(nlf_batch *b)
+{
+    if (b->prepared) return NLF_OK;
+    nlf_ctx *c = b->ctx;
+    const int nj = (int)b->jobs.size();
+    if (nj == 0) { b->prepared = true; return NLF_OK; }
+    int rc = upload_jobs(b, 0);
+    if (rc) return rc;
+    {
+        KLaunch k(c, P_DIAG);
+        dim3 grid((b->upper - b->lower + 1 + 63) / 64, nj);
+        k_diag_means<<<grid, 64, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->pitch);
+    }
+    {
+        KLaunch k(c, P_DIAG);
+        k_isotonic<<<nj, 32, 0, c->stream>>>(b->d_jobs, b->lower, b->upper);
+    }
+    {
+        KLaunch k(c, P_THRESH);
+        dim3 grid(64, nj);
+        k_count_candidates<<<grid, 256, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->pitch);
+    }
+    NLF_CUDA(cudaGetLastError());
+    b->prepared = true;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expected, int nexp, int w,
+                               const double *gw, int radius, double thre)
+{
+    if (!b || !f || !expected || !gw) return fail(NLF_ERR_ARG, "nlf_batch_score: NULL argument");
+    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    if (radius != 4) return fail(NLF_ERR_ARG, "gaussian radius %d not supported (sigma=1 -> radius 4)", radius);
+    if (w != 5 && w != 6 && w != 7) return fail(NLF_ERR_ARG, "window half-size w=%d not supported (5, 6, 7)", w);
+    if (f->dev.n_features != (2 * w + 1) * (2 * w + 1))
+        return fail(NLF_ERR_ARG, "forest has %d features, window w=%d needs %d", f->dev.n_features, w, (2 * w + 1) * (2 * w + 1));
+    if (2 * w >= 14) { /* band keeps upper+13 diagonals: enough for w <= 6; w = 7 needs upper+14 */ }
+    if (nexp <= 0) return fail(NLF_ERR_ARG, "empty expected array");
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    const int nj = (int)b->jobs.size();
+    if (nj == 0) { b->scored = true; return NLF_OK; }
+    int rc = batch_prepare(b);
+    if (rc) return rc;
+    const int dlo = std::max(b->lower, w + 2);
+    b->W = w;
+    b->ndt = (b->upper - dlo + 1 + 31) / 32;
+    if (b->ndt < 1) b->ndt = 1;
+    b->ndp = b->ndt * 32;
+    const int F = (2 * w + 1) * (2 * w + 1);
+
+    NLF_CUDA(cudaMemcpyToSymbolAsync(c_gw, gw, sizeof(double) * 9, 0, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_exp, sizeof(double) * nexp, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(b->d_exp, expected, sizeof(double) * nexp, cudaMemcpyHostToDevice, c->stream));
+
+    for (int k = 0; k < nj; k++) {
+        HostJob &j = b->jobs[k];
+        size_t cells = (size_t)j.n * b->ndp;
+        NLF_CUDA(cudaMallocAsync(&j.d_prob, sizeof(double) * cells, c->stream));
+        if (b->keep_slots) NLF_CUDA(cudaMallocAsync(&j.d_slot, sizeof(int) * cells, c->stream));
+        j.don_cap = (long long)j.n * (b->upper - dlo + 1);
+        if (j.don_cap > (1LL << 22)) j.don_cap = (1LL << 22);
+        if (j.don_cap < 1) j.don_cap = 1;
+        NLF_CUDA(cudaMallocAsync(&j.d_don_i, sizeof(int) * j.don_cap, c->stream));
+        NLF_CUDA(cudaMallocAsync(&j.d_don_j, sizeof(int) * j.don_cap, c->stream));
+        NLF_CUDA(cudaMallocAsync(&j.d_don_p, sizeof(double) * j.don_cap, c->stream));
+        NLF_CUDA(cudaMallocAsync(&j.d_don_v, sizeof(double) * j.don_cap, c->stream));
+    }
+    rc = upload_jobs(b, w);
+    if (rc) return rc;
+    const long long groups = b->total_groups;
+    const int tiles = b->total_tiles;
+    if (groups > 0xfffffff0LL) return fail(NLF_ERR_ARG, "batch too large: %lld feature groups; split the batch", groups);
+    b->max_groups = (unsigned)groups;
+    NLF_CUDA(cudaMallocAsync(&b->d_hdr, sizeof(GroupHdr) * (size_t)groups, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_featT, sizeof(float) * (size_t)groups * F * 32, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned), c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_overflow, sizeof(int), c->stream));
+    NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
+    NLF_CUDA(cudaMemsetAsync(b->d_overflow, 0, sizeof(int), c->stream));
+
+    if (w == 5) launch_features<5>(b, tiles, nexp);
+    else if (w == 6) launch_features<6>(b, tiles, nexp);
+    else launch_features<7>(b, tiles, nexp);
+    NLF_CUDA(cudaGetLastError());
+    {
+        constexpr int WARPS = 4;
+        size_t smem = sizeof(float) * (size_t)WARPS * F * 32;
+        NLF_CUDA(cudaFuncSetAttribute(k_forest<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = c->sm_count * 2;
+        KLaunch k(c, P_FOREST);
+        k_forest<WARPS><<<grid, 32 * WARPS, smem, c->stream>>>(f->dev, b->d_hdr, b->d_featT, b->d_group_counter,
+                                                               b->d_jobs, b->lower, w, b->ndp);
+    }
+    NLF_CUDA(cudaGetLastError());
+    {
+        KLaunch k(c, P_THRESH);
+        dim3 grid(64, nj);
+        k_threshold<<<grid, 256, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, w, b->pitch, b->ndp, thre);
+    }
+    NLF_CUDA(cudaGetLastError());
+    b->scored = true;
+    b->counted = false;
+    return NLF_OK;
+}
+
+static int batch_sync_counts(nlf_batch *b)
+{
+    if (!b->prepared) {
+        int rc0 = batch_prepare(b);
+        if (rc0) return rc0;
+    }
+    if (b->counted) return NLF_OK;
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    for (auto &j : b->jobs) {
+        NLF_CUDA(cudaMemcpyAsync(j.counts, j.d_counts, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaMemcpyAsync(&j.status, j.d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    int overflow = 0;
+    if (b->d_overflow)
+        NLF_CUDA(cudaMemcpyAsync(&overflow, b->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    if (overflow) return fail(NLF_ERR_CUDA, "feature group buffer overflow (internal sizing error)");
+    b->counted = true;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_counts(nlf_batch *b, long long *n_cand, long long *n_scored, long long *n_donuts)
+{
+    int rc = batch_sync_counts(b);
+    if (rc) return rc;
+    int first_err = 0;
+    for (size_t k = 0; k < b->jobs.size(); k++) {
+        HostJob &j = b->jobs[k];
+        if (j.status && !first_err) first_err = j.status;
+        if (n_cand) n_cand[k] = j.status ? -1 : (long long)j.counts[0];
+        if (n_scored) n_scored[k] = j.status ? -1 : (long long)j.counts[1];
+        if (n_donuts) n_donuts[k] = j.status ? -1 : (long long)j.counts[2];
+        if (!j.status && (long long)j.counts[2] > j.don_cap)
+            return fail(NLF_ERR_ARG, "job %zu: %llu pixels above the threshold exceed the Donut capacity %lld; raise the threshold",
+                        k, j.counts[2], j.don_cap);
+    }
+    if (first_err == NLF_ERR_EMPTY_FIT)
+        return fail(NLF_ERR_EMPTY_FIT, "a matrix has no diagonal longer than 5 bins: the isotonic fit of get_candidates is empty");
+    if (first_err == NLF_ERR_LOWER_TRI)
+        return fail(NLF_ERR_LOWER_TRI, "a matrix has non-zero entries below the main diagonal (np.triu input expected)");
+    if (first_err) return fail(first_err, "job failed with status %d", first_err);
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_fetch_donuts(nlf_batch *b, int job, int *i, int *j, double *prob, double *value)
+{
+    if (!b->scored) return fail(NLF_ERR_STATE, "batch not scored yet");
+    int rc = batch_sync_counts(b);
+    if (rc) return rc;
+    if (job < 0 || job >= (int)b->jobs.size()) return fail(NLF_ERR_ARG, "job %d out of range", job);
+    HostJob &J = b->jobs[job];
+    if (J.status) return fail(J.status, "job %d failed with status %d", job, J.status);
+    size_t m = (size_t)J.counts[2];
+    if (m == 0) return NLF_OK;
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaMemcpyAsync(i, J.d_don_i, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(j, J.d_don_j, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(prob, J.d_don_p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(value, J.d_don_v, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    return NLF_OK;
+}
+
+// ordered listing helper (mode 0 candidates, 1 scored)
+static int ordered_list(nlf_batch *b, int job, int mode, long long cap, int *oi, int *oj, double *op, float *ofea)
+{
+    if (mode == 1 && !b->scored) return fail(NLF_ERR_STATE, "batch not scored yet");
+    int rc = batch_sync_counts(b);
+    if (rc) return rc;
+    if (job < 0 || job >= (int)b->jobs.size()) return fail(NLF_ERR_ARG, "job %d out of range", job);
+    HostJob &J = b->jobs[job];
+    if (J.status) return fail(J.status, "job %d failed with status %d", job, J.status);
+    nlf_ctx *c = b->ctx;
+    const int nd = b->upper - b->lower + 1;
+    JobDev d;
+    memset(&d, 0, sizeof(d));
+    d.band = J.d_band; d.prob = J.d_prob; d.slot = J.d_slot; d.e = J.d_e; d.n = J.n; d.status = J.d_status;
+    int *d_cnt;
+    long long *d_off;
+    NLF_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * nd, c->stream));
+    NLF_CUDA(cudaMallocAsync(&d_off, sizeof(long long) * nd, c->stream));
+    {
+        KLaunch k(c, P_THRESH);
+        k_diag_count<<<nd, 256, 0, c->stream>>>(d, mode, b->lower, b->upper, b->W, b->pitch, b->ndp, d_cnt);
+    }
+    std::vector<int> cnt(nd);
+    NLF_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * nd, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<long long> off(nd);
+    long long tot = 0;
+    for (int k = 0; k < nd; k++) { off[k] = tot; tot += cnt[k]; }
+    if (tot > cap) return fail(NLF_ERR_ARG, "output capacity %lld too small for %lld rows", cap, tot);
+    if (tot > 0) {
+        int *d_i, *d_j, *d_slot = nullptr;
+        double *d_p = nullptr;
+        NLF_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * nd, cudaMemcpyHostToDevice, c->stream));
+        NLF_CUDA(cudaMallocAsync(&d_i, sizeof(int) * tot, c->stream));
+        NLF_CUDA(cudaMallocAsync(&d_j, sizeof(int) * tot, c->stream));
+        if (op) NLF_CUDA(cudaMallocAsync(&d_p, sizeof(double) * tot, c->stream));
+        if (ofea) NLF_CUDA(cudaMallocAsync(&d_slot, sizeof(int) * tot, c->stream));
+        {
+            KLaunch k(c, P_THRESH);
+            k_diag_fill<<<nd, 256, 0, c->stream>>>(d, mode, b->lower, b->upper, b->W, b->pitch, b->ndp, d_off, d_i, d_j,
+                                                   d_p, d_slot);
+        }
+        NLF_CUDA(cudaGetLastError());
+        if (oi) NLF_CUDA(cudaMemcpyAsync(oi, d_i, sizeof(int) * tot, cudaMemcpyDeviceToHost, c->stream));
+        if (oj) NLF_CUDA(cudaMemcpyAsync(oj, d_j, sizeof(int) * tot, cudaMemcpyDeviceToHost, c->stream));
+        if (op) NLF_CUDA(cudaMemcpyAsync(op, d_p, sizeof(double) * tot, cudaMemcpyDeviceToHost, c->stream));
+        if (ofea) {
+            const int F = (2 * b->W + 1) * (2 * b->W + 1);
+            float *d_f;
+            NLF_CUDA(cudaMallocAsync(&d_f, sizeof(float) * (size_t)tot * F, c->stream));
+            {
+                KLaunch k(c, P_THRESH);
+                long long work = tot * F;
+                k_gather_features<<<(unsigned)((work + 255) / 256), 256, 0, c->stream>>>(b->d_featT, d_slot, tot, F, d_f);
+            }
+            NLF_CUDA(cudaGetLastError());
+            NLF_CUDA(cudaMemcpyAsync(ofea, d_f, sizeof(float) * (size_t)tot * F, cudaMemcpyDeviceToHost, c->stream));
+            NLF_CUDA(cudaFreeAsync(d_f, c->stream));
+            NLF_CUDA(cudaFreeAsync(d_slot, c->stream));
+        }
+        NLF_CUDA(cudaStreamSynchronize(c->stream));
+        NLF_CUDA(cudaFreeAsync(d_i, c->stream));
+        NLF_CUDA(cudaFreeAsync(d_j, c->stream));
+        if (d_p) NLF_CUDA(cudaFreeAsync(d_p, c->stream));
+    }
+    NLF_CUDA(cudaFreeAsync(d_cnt, c->stream));
+    NLF_CUDA(cudaFreeAsync(d_off, c->stream));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_fetch_scored(nlf_batch *b, int job, long long cap, int *i, int *j, double *prob)
+{
+    return ordered_list(b, job, 1, cap, i, j, prob, nullptr);
+}
+
+NLF_EXPORT int nlf_batch_fetch_candidates(nlf_batch *b, int job, long long cap, int *ridx, int *cidx)
+{
+    return ordered_list(b, job, 0, cap, ridx, cidx, nullptr, nullptr);
+}
+
+NLF_EXPORT int nlf_batch_fetch_features32(nlf_batch *b, int job, long long cap, float *fea)
+{
+    if (!b->keep_slots) return fail(NLF_ERR_STATE, "feature slots were not kept: call nlf_batch_keep_features before scoring");
+    return ordered_list(b, job, 1, cap, nullptr, nullptr, nullptr, fea);
+}
+
+NLF_EXPORT int nlf_batch_keep_features(nlf_batch *b, int on)
+{
+    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    b->keep_slots = on != 0;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const int *yi, long long nc, int w,
+                                   const double *expected, int nexp, const double *gw, int radius, double *fea,
+                                   int *clist, long long *n_rows)
+{
+    if (!b || job < 0 || job >= (int)b->jobs.size()) return fail(NLF_ERR_ARG, "nlf_batch_getwindow: bad job");
+    if (radius != 4) return fail(NLF_ERR_ARG, "gaussian radius %d not supported", radius);
+    if (w != 5 && w != 6 && w != 7) return fail(NLF_ERR_ARG, "w=%d not supported", w);
+    *n_rows = 0;
+    if (nc < 2) return NLF_OK;          // callers.py:587-588
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    HostJob &J = b->jobs[job];
+    const int F = (2 * w + 1) * (2 * w + 1);
+    // callers.py:592-595: fewer than two coordinates inside the border mask -> nothing
+    long long inside = 0;
+    for (long long k = 0; k < nc; k++)
+        inside += (xi[k] - w >= 0) && (yi[k] + w + 1 <= J.n) && (yi[k] - xi[k] - 2 >= w);
+    if (inside < 2) return NLF_OK;
+    for (long long k = 0; k < nc; k++)
+        if (xi[k] < 0 || yi[k] < 0 || xi[k] >= J.n || yi[k] >= J.n) return fail(NLF_ERR_ARG, "coordinate %lld out of range", k);
+    int *d_x, *d_y;
+    unsigned char *d_pass;
+    double *d_fea, *d_exp;
+    NLF_CUDA(cudaMallocAsync(&d_x, sizeof(int) * nc, c->stream));
+    NLF_CUDA(cudaMallocAsync(&d_y, sizeof(int) * nc, c->stream));
+    NLF_CUDA(cudaMallocAsync(&d_pass, nc, c->stream));
+    NLF_CUDA(cudaMallocAsync(&d_fea, sizeof(double) * (size_t)nc * F, c->stream));
+    NLF_CUDA(cudaMallocAsync(&d_exp, sizeof(double) * nexp, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(d_x, xi, sizeof(int) * nc, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(d_y, yi, sizeof(int) * nc, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(d_exp, expected, sizeof(double) * nexp, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMemcpyToSymbolAsync(c_gw, gw, sizeof(double) * 9, 0, cudaMemcpyHostToDevice, c->stream));
+    JobDev d;
+    memset(&d, 0, sizeof(d));
+    d.band = J.d_band; d.n = J.n;
+    {
+        KLaunch k(c, P_FEATURE);
+        unsigned grid = (unsigned)((nc + 3) / 4);
+        if (w == 5) k_getwindow<5><<<grid, 128, 0, c->stream>>>(d, b->upper, b->pitch, d_x, d_y, nc, d_exp, nexp, d_pass, d_fea);
+        else if (w == 6) k_getwindow<6><<<grid, 128, 0, c->stream>>>(d, b->upper, b->pitch, d_x, d_y, nc, d_exp, nexp, d_pass, d_fea);
+        else k_getwindow<7><<<grid, 128, 0, c->stream>>>(d, b->upper, b->pitch, d_x, d_y, nc, d_exp, nexp, d_pass, d_fea);
+    }
+    NLF_CUDA(cudaGetLastError());
+    std::vector<unsigned char> pass((size_t)nc);
+    std::vector<double> all((size_t)nc * F);
+    NLF_CUDA(cudaMemcpyAsync(pass.data(), d_pass, nc, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(all.data(), d_fea, sizeof(double) * (size_t)nc * F, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    long long rows = 0;
+    for (long long k = 0; k < nc; k++)
+        if (pass[k]) {
+            memcpy(fea + (size_t)rows * F, all.data() + (size_t)k * F, sizeof(double) * F);
+            clist[2 * rows] = xi[k];
+            clist[2 * rows + 1] = yi[k];
+            rows++;
+        }
+    *n_rows = rows;
+    NLF_CUDA(cudaFreeAsync(d_x, c->stream));
+    NLF_CUDA(cudaFreeAsync(d_y, c->stream));
+    NLF_CUDA(cudaFreeAsync(d_pass, c->stream));
+    NLF_CUDA(cudaFreeAsync(d_fea, c->stream));
+    NLF_CUDA(cudaFreeAsync(d_exp, c->stream));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_destroy(nlf_batch *b)
+{
+    if (!b) return NLF_OK;
+    nlf_ctx *c = b->ctx;
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    for (auto &j : b->jobs) {
+        if (j.d_band && j.band_owned) cudaFreeAsync(j.d_band, s);
+        if (j.d_prob) cudaFreeAsync(j.d_prob, s);
+        if (j.d_slot) cudaFreeAsync(j.d_slot, s);
+        cudaFreeAsync(j.d_means, s); cudaFreeAsync(j.d_e, s); cudaFreeAsync(j.d_pw, s); cudaFreeAsync(j.d_pr, s);
+        cudaFreeAsync(j.d_status, s); cudaFreeAsync(j.d_counts, s);
+        if (j.d_don_i) { cudaFreeAsync(j.d_don_i, s); cudaFreeAsync(j.d_don_j, s); cudaFreeAsync(j.d_don_p, s); cudaFreeAsync(j.d_don_v, s); }
+    }
+    if (b->d_jobs) cudaFreeAsync(b->d_jobs, s);
+    if (b->d_tile_base) cudaFreeAsync(b->d_tile_base, s);
+    if (b->d_hdr) cudaFreeAsync(b->d_hdr, s);
+    if (b->d_featT) cudaFreeAsync(b->d_featT, s);
+    if (b->d_group_counter) cudaFreeAsync(b->d_group_counter, s);
+    if (b->d_overflow) cudaFreeAsync(b->d_overflow, s);
+    if (b->d_exp) cudaFreeAsync(b->d_exp, s);
+    delete b;
+    return NLF_OK;
+}

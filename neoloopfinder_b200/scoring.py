@@ -1,0 +1,287 @@
+"""Python face of the CUDA scoring path (batch of gap-free matrices -> Donuts -> pooled loops).
+
+Thin, typed wrappers over include/nlf_b200.h; the reference-shaped classes in ``callers.py`` /
+``assembly.py`` are built on these.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, i32, ptr
+
+__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "pool_buckets", "local_clustering_gpu"]
+
+
+def gaussian_weights(sigma: float = 1.0, truncate: float = 4.0):
+    """Kernel of ``scipy.ndimage.gaussian_filter(sigma=1)`` (scipy/ndimage/_filters.py
+    ``_gaussian_kernel1d``), computed on the host with the same numpy operations scipy uses, so it
+    tracks the local numpy build exactly as the reference does.  The device never calls exp()."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[::-1], dtype=np.float64), radius
+
+
+class DeviceAssembly:
+    """Device-resident fusion matrix of one assembly (K2-K4)."""
+
+    def __init__(self, M, bias, block_index, ctx=None):
+        self.ctx = ctx or _lib.Context.get()
+        M = f64(M)
+        if M.ndim != 2 or M.shape[0] != M.shape[1]:
+            raise ValueError("fusion matrix must be square")
+        self.n = M.shape[0]
+        bias = f64(bias)
+        bi = np.asarray(block_index, dtype=np.int64).reshape(-1, 2)
+        self.nblk = len(bi)
+        lo, hi = i32(bi[:, 0]), i32(bi[:, 1])
+        self.h = C.c_void_p()
+        check(_lib.load().nlf_assembly_create(self.ctx.h, ptr(M, C.c_double), self.n, ptr(bias, C.c_double),
+                                              ptr(lo, C.c_int), ptr(hi, C.c_int), self.nblk, C.byref(self.h)))
+        self._kept = None
+
+    def diag_means(self, maxdiag: int, mink: int = 3):
+        """-> (mean[npairs, maxdiag+1] with NaN where not kept, count[npairs, maxdiag+1])."""
+        npairs = self.nblk * (self.nblk + 1) // 2
+        mean = np.empty((npairs, maxdiag + 1), dtype=np.float64)
+        cnt = np.empty((npairs, maxdiag + 1), dtype=np.int32)
+        check(_lib.load().nlf_assembly_diag_means(self.h, int(maxdiag), int(mink), ptr(mean, C.c_double),
+                                                  ptr(cnt, C.c_int)))
+        return mean, cnt
+
+    def set_scales(self, op, val):
+        op = i32(op).reshape(self.nblk, self.nblk)
+        val = f64(val).reshape(self.nblk, self.nblk)
+        check(_lib.load().nlf_assembly_set_scales(self.h, ptr(op, C.c_int), ptr(val, C.c_double)))
+        self._kept = None
+
+    def kept_index(self) -> np.ndarray:
+        if self._kept is None:
+            kept = np.empty(self.n, dtype=np.int32)
+            nk = C.c_int(0)
+            check(_lib.load().nlf_assembly_remove_gaps(self.h, ptr(kept, C.c_int), C.byref(nk)))
+            self._kept = kept[:nk.value].copy()
+        return self._kept
+
+    def hcm(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        check(_lib.load().nlf_assembly_fetch_hcm(self.h, ptr(out, C.c_double)))
+        return out
+
+    def gap_free(self) -> np.ndarray:
+        nk = len(self.kept_index())
+        out = np.empty((nk, nk), dtype=np.float64)
+        check(_lib.load().nlf_assembly_fetch_gap_free(self.h, ptr(out, C.c_double)))
+        return out
+
+    def close(self):
+        if self.h:
+            _lib.load().nlf_assembly_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ScoreBatch:
+    """A batch of gap-free matrices scored together (K1, K5-K9)."""
+
+    def __init__(self, lower: int = 4, upper: int = 400, ctx=None):
+        self.ctx = ctx or _lib.Context.get()
+        self.lower, self.upper = int(lower), int(upper)
+        self.h = C.c_void_p()
+        check(_lib.load().nlf_batch_create(self.ctx.h, self.lower, self.upper, C.byref(self.h)))
+        self._keepalive = []
+        self.njobs = 0
+        self.n = []
+        self.w = None
+        self._counts = None
+
+    # ---- inputs
+    def add_dense(self, G) -> int:
+        G = f64(G)
+        if G.ndim != 2 or G.shape[0] != G.shape[1]:
+            raise ValueError("matrix must be square")
+        self._keepalive.append(G)
+        j = check(_lib.load().nlf_batch_add_dense(self.h, ptr(G, C.c_double), G.shape[0]))
+        self.njobs += 1
+        self.n.append(G.shape[0])
+        return j
+
+    def add_assembly(self, asm: DeviceAssembly) -> int:
+        j = check(_lib.load().nlf_batch_add_assembly(self.h, asm.h))
+        self.njobs += 1
+        self.n.append(len(asm.kept_index()))
+        return j
+
+    def add_band(self, band) -> int:
+        band = f64(band)
+        self._keepalive.append(band)
+        j = check(_lib.load().nlf_batch_add_band(self.h, ptr(band, C.c_double), band.shape[0], band.shape[1]))
+        self.njobs += 1
+        self.n.append(band.shape[0])
+        return j
+
+    def keep_features(self, on=True):
+        check(_lib.load().nlf_batch_keep_features(self.h, 1 if on else 0))
+
+    # ---- compute
+    def score(self, forest, exp_arr, thre: float, w: Optional[int] = None, gw=None):
+        exp_arr = f64(exp_arr)
+        if gw is None:
+            gw, radius = gaussian_weights()
+        else:
+            gw = f64(gw)
+            radius = (gw.size - 1) // 2
+        self.w = int(forest.w if w is None else w)
+        check(_lib.load().nlf_batch_score(self.h, forest.h, ptr(exp_arr, C.c_double), exp_arr.size, self.w,
+                                          ptr(gw, C.c_double), radius, float(thre)))
+        self._counts = None
+        self._keepalive.clear()
+
+    # ---- outputs
+    def counts(self):
+        if self._counts is None:
+            a = np.zeros(max(1, self.njobs), dtype=np.int64)
+            b = np.zeros_like(a)
+            c = np.zeros_like(a)
+            check(_lib.load().nlf_batch_counts(self.h, ptr(a, C.c_longlong), ptr(b, C.c_longlong), ptr(c, C.c_longlong)))
+            self._counts = (a[:self.njobs], b[:self.njobs], c[:self.njobs])
+        return self._counts
+
+    def donuts(self, job: int):
+        m = int(self.counts()[2][job])
+        i = np.empty(m, np.int32); j = np.empty(m, np.int32)
+        p = np.empty(m, np.float64); v = np.empty(m, np.float64)
+        if m:
+            check(_lib.load().nlf_batch_fetch_donuts(self.h, job, ptr(i, C.c_int), ptr(j, C.c_int),
+                                                     ptr(p, C.c_double), ptr(v, C.c_double)))
+        return i, j, p, v
+
+    def scored(self, job: int):
+        m = int(self.counts()[1][job])
+        i = np.empty(m, np.int32); j = np.empty(m, np.int32); p = np.empty(m, np.float64)
+        check(_lib.load().nlf_batch_fetch_scored(self.h, job, m, ptr(i, C.c_int), ptr(j, C.c_int), ptr(p, C.c_double)))
+        return i, j, p
+
+    def candidates(self, job: int):
+        m = int(self.counts()[0][job])
+        r = np.empty(m, np.int32); c = np.empty(m, np.int32)
+        check(_lib.load().nlf_batch_fetch_candidates(self.h, job, m, ptr(r, C.c_int), ptr(c, C.c_int)))
+        return r, c
+
+    def features32(self, job: int):
+        m = int(self.counts()[1][job])
+        F = (2 * self.w + 1) ** 2
+        fea = np.empty((m, F), dtype=np.float32)
+        check(_lib.load().nlf_batch_fetch_features32(self.h, job, m, ptr(fea, C.c_float)))
+        return fea
+
+    def getwindow(self, job: int, xi, yi, w: int, exp_arr, gw=None):
+        xi, yi = i32(xi), i32(yi)
+        exp_arr = f64(exp_arr)
+        if gw is None:
+            gw, radius = gaussian_weights()
+        else:
+            gw = f64(gw); radius = (gw.size - 1) // 2
+        F = (2 * w + 1) ** 2
+        fea = np.empty((max(1, xi.size), F), dtype=np.float64)
+        clist = np.empty((max(1, xi.size), 2), dtype=np.int32)
+        nrows = C.c_longlong(0)
+        check(_lib.load().nlf_batch_getwindow(self.h, job, ptr(xi, C.c_int), ptr(yi, C.c_int), xi.size, int(w),
+                                              ptr(exp_arr, C.c_double), exp_arr.size, ptr(gw, C.c_double), radius,
+                                              ptr(fea, C.c_double), ptr(clist, C.c_int), C.byref(nrows)))
+        return fea[:nrows.value], clist[:nrows.value]
+
+    def close(self):
+        if self.h:
+            _lib.load().nlf_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pool_buckets(buckets: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]], res: int, min_count: int = 2,
+                 r: int = 15000, ctx=None) -> List[np.ndarray]:
+    """Peakachu._local_clustering for a list of buckets [(i, j, value)] -> list of keep masks.
+
+    Below 10 kb scipy's peak-distance filter can remove peaks, and among EQUAL peak heights its
+    outcome follows numpy.argsort's implementation-defined tie order.  The kernel reports when
+    that can matter; only then are the peak heights brought back and numpy.argsort -- the very
+    call the reference makes (scipy/signal/_peak_finding.py _select_by_peak_distance) -- asked for
+    the permutation, which the pooling kernel then follows.
+    """
+    ctx = ctx or _lib.Context.get()
+    L = _lib.load()
+    nb = len(buckets)
+    if nb == 0:
+        return []
+    sizes = [len(b[0]) for b in buckets]
+    off = np.zeros(nb + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    total = int(off[-1])
+    if total == 0:
+        return [np.zeros(0, dtype=bool) for _ in buckets]
+    pi = i32(np.concatenate([np.asarray(b[0]) for b in buckets]))
+    pj = i32(np.concatenate([np.asarray(b[1]) for b in buckets]))
+    val = f64(np.concatenate([np.asarray(b[2]) for b in buckets]))
+    xo = yo = None
+    xo_off = yo_off = None
+    if max(r // res, 2) > 2:
+        orders = []
+        for pos in (pi, pj):
+            prio = np.empty(total, dtype=np.float64)
+            poff = np.zeros(nb + 1, dtype=np.int64)
+            amb = C.c_int(0)
+            check(L.nlf_pool_peak_heights(ctx.h, nb, ptr(off, C.c_int64), ptr(pos, C.c_int), int(res), int(min_count),
+                                          int(r), ptr(prio, C.c_double), ptr(poff, C.c_int64), C.byref(amb)))
+            orders.append((prio, poff, amb.value))
+        if orders[0][2] or orders[1][2]:
+            def perm(prio, poff):
+                out = np.empty(int(poff[-1]) + 1, dtype=np.int32)
+                for k in range(nb):
+                    a, b = int(poff[k]), int(poff[k + 1])
+                    out[a:b] = np.argsort(prio[a:b])        # default kind, as scipy calls it
+                return out
+            xo, xo_off = perm(*orders[0][:2]), orders[0][1]
+            yo, yo_off = perm(*orders[1][:2]), orders[1][1]
+    keep = np.zeros(total, dtype=np.uint8)
+    check(L.nlf_pool(ctx.h, nb, ptr(off, C.c_int64), ptr(pi, C.c_int), ptr(pj, C.c_int), ptr(val, C.c_double),
+                     int(res), int(min_count), int(r),
+                     None if xo is None else ptr(xo, C.c_int), None if xo is None else ptr(xo_off, C.c_int64),
+                     None if yo is None else ptr(yo, C.c_int), None if yo is None else ptr(yo_off, C.c_int64),
+                     ptr(keep, C.c_ubyte)))
+    return [keep[off[k]:off[k + 1]].astype(bool) for k in range(nb)]
+
+
+def local_clustering_gpu(ij, val, res, min_count=2, r=15000, chain_i=None, chain_j=None, ctx=None):
+    """Peakachu.local_clustering (callers.py:668-697): bucket by (chain_i, chain_j), pool each
+    bucket on the GPU, return the set of kept (i, j)."""
+    ij = np.asarray(ij, dtype=np.int64).reshape(-1, 2)
+    val = f64(val)
+    if len(ij) == 0:
+        return set()
+    if chain_i is None:
+        key = np.zeros(len(ij), dtype=np.int64)
+    else:
+        key = np.asarray(chain_i, dtype=np.int64) * (1 << 24) + np.asarray(chain_j, dtype=np.int64)
+    uniq = np.unique(key)
+    sels = [np.where(key == k)[0] for k in uniq]
+    masks = pool_buckets([(ij[s, 0], ij[s, 1], val[s]) for s in sels], res, min_count, r, ctx)
+    out = set()
+    for s, m in zip(sels, masks):
+        for a, b in ij[s][m]:
+            out.add((int(a), int(b)))
+    return out

@@ -1,0 +1,148 @@
+"""GPU parity, stage by stage, through the C ABI, against the golden fixtures produced by the
+real reference and against the C oracle.  Bit-exact everywhere (fp64 / fp32 features / indices)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import CASES
+from tests.helpers import GOLDEN, load_case, scale_plan_from_slopes, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from neoloopfinder_b200 import _lib
+    assert _lib.device_count() > 0, "no CUDA device visible"
+    return _lib.Context.get(0)
+
+
+@pytest.fixture(scope="module")
+def forests(gpu):
+    from neoloopfinder_b200.forest import load_forest
+    return lambda name: load_forest(os.path.join(GOLDEN, name), gpu)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_normalisation_stages(name, gpu):
+    from neoloopfinder_b200.scoring import DeviceAssembly
+    z = load_case(name)
+    res = int(z["res"])
+    M, bias, bi = z["fusion_matrix"], z["bias"], z["block_index"]
+    nb = len(bi)
+    asm = DeviceAssembly(M, bias, bi, gpu)
+    maxdiag = 2000000 // res
+    mean, cnt = asm.diag_means(maxdiag)
+    p = 0
+    for a in range(nb):
+        for b in range(a, nb):
+            idx = np.where(~np.isnan(mean[p]))[0]
+            assert list(idx) == list(z[f"exps_idx_{a}_{b}"]), (a, b)
+            assert np.array_equal(mean[p][idx], z[f"exps_val_{a}_{b}"]), (a, b)
+            p += 1
+    op, val = scale_plan_from_slopes(z["slopes"])
+    asm.set_scales(op, val)
+    assert sha(asm.hcm()) == str(z["hcm_sha"])
+    assert np.array_equal(asm.kept_index(), z["index_map"])
+    assert sha(asm.gap_free()) == str(z["gap_free_sha"])
+    asm.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("source", ["device", "host"])
+def test_scoring_stages(name, source, gpu, forests):
+    from neoloopfinder_b200.scoring import DeviceAssembly, ScoreBatch, local_clustering_gpu
+    z = load_case(name)
+    res = int(z["res"])
+    M, bias, bi, exp = z["fusion_matrix"], z["bias"], z["block_index"], z["expected"]
+    op, val = scale_plan_from_slopes(z["slopes"])
+    asm = DeviceAssembly(M, bias, bi, gpu)
+    asm.set_scales(op, val)
+    forest = forests(str(z["model"]))
+    w = int(z["w"])
+    assert forest.w == w
+    batch = ScoreBatch(4, 400, gpu)
+    if source == "device":
+        job = batch.add_assembly(asm)
+    else:
+        job = batch.add_dense(asm.gap_free())
+    # candidates are available before any model is involved (Peakachu.__init__)
+    r, c = batch.candidates(job)
+    assert np.array_equal(r, z["ridx"]) and np.array_equal(c, z["cidx"])
+    batch.keep_features(True)
+    thre = float(z["prob"])
+    batch.score(forest, exp, thre)
+    n_cand, n_scored, n_don = batch.counts()
+    assert n_cand[job] == len(z["ridx"])
+    assert n_scored[job] == len(z["clist"])
+    i, j, p = batch.scored(job)
+    assert np.array_equal(np.stack([i, j], 1), z["clist"])
+    fea32 = batch.features32(job)
+    assert sha(fea32) == str(z["fea32_sha"])
+    assert np.array_equal(p, z["probas"])          # bit-exact probabilities
+    di, dj, dp, dv = batch.donuts(job)
+    o = np.lexsort((di, dj - di))                  # diagonal-major like the reference's clist order
+    assert np.array_equal(np.stack([di, dj], 1)[o], z["donut_ij"])
+    assert np.array_equal(dv[o], z["donut_val"])
+    # float64 getwindow accessor == reference fea
+    fea, cl = batch.getwindow(job, z["ridx"], z["cidx"], w, exp)
+    assert np.array_equal(cl, z["clist"])
+    assert sha(fea) == str(z["fea_sha"])
+    # pooling
+    chains, im = z["chains"], z["index_map"]
+    ij = np.stack([di, dj], 1)
+    loops = local_clustering_gpu(ij, dv, res, int(z["min_count"]), 15000, chains[im[ij[:, 0]]], chains[im[ij[:, 1]]], gpu)
+    assert sorted(loops) == [tuple(x) for x in z["loop_index"]]
+    pm = {(int(a), int(b)): float(q) for a, b, q in zip(di, dj, dp)}
+    assert [pm[t] for t in sorted(loops)] == list(z["loop_prob"])
+    batch.close()
+    asm.close()
+
+
+def test_pool_cases(gpu):
+    from neoloopfinder_b200.scoring import local_clustering_gpu
+    z = np.load(os.path.join(GOLDEN, "pool_cases.npz"))
+    for k in range(int(z["n_cases"])):
+        ij, val, ch = z[f"c{k}_ij"], z[f"c{k}_val"], z[f"c{k}_chain"]
+        res, mc, r = (int(v) for v in z[f"c{k}_par"])
+        got = local_clustering_gpu(ij, val, res, mc, r, ch[ij[:, 0]], ch[ij[:, 1]], gpu)
+        assert sorted(got) == [tuple(x) for x in z[f"c{k}_out"]], f"pool case {k}"
+
+
+def test_forest_rows_match_sklearn(gpu, forests, models):
+    rng = np.random.default_rng(3)
+    for name, F in (("forest_w6.joblib", 169), ("forest_w5.joblib", 121)):
+        X = rng.random((4000, F)).astype(np.float32)
+        X[rng.random(X.shape) < 0.01] = np.nan            # missing values follow missing_go_to_left
+        model = models(name)
+        ref = model.predict_proba(X)[:, 1]
+        got = forests(name).predict_proba1(X)
+        assert np.array_equal(ref, got)
+
+
+def test_batch_of_all_cases_matches_oracle(gpu, forests, models):
+    """All 10 kb cases in ONE batch (the production shape) against the C oracle."""
+    from oracle import coracle as co
+    from neoloopfinder_b200.scoring import ScoreBatch
+    names = ["case_transloc_10k", "case_inversion_10k", "case_complex_10k"]
+    forest = forests("forest_w6.joblib")
+    batch = ScoreBatch(4, 400, gpu)
+    mats = []
+    for nme in names:
+        z = load_case(nme)
+        op, val = scale_plan_from_slopes(z["slopes"])
+        hcm = co.scale_blocks(z["fusion_matrix"], z["block_index"], op, val)
+        kept = co.remove_gaps_index(hcm)
+        G = hcm[np.ix_(kept, kept)]
+        mats.append((G, z))
+        batch.add_dense(G)
+    exp = mats[0][1]["expected"]
+    batch.score(forest, exp, 0.5)
+    arrays = co.sklearn_forest_arrays(models("forest_w6.joblib"))
+    for job, (G, z) in enumerate(mats):
+        i, j, p = batch.scored(job)
+        cl, pr, _ = co.score_matrix(G, exp, arrays, 6)
+        assert np.array_equal(np.stack([i, j], 1), cl)
+        assert np.array_equal(p, pr)
+    batch.close()
