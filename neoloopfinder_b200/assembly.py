@@ -1,0 +1,290 @@
+"""Drop-in for ``neoloop.assembly.complexSV`` on the neoloop-caller path (neoloop/assembly.py:278-596).
+
+Host side: parsing of the assembly line, block geometry, the cooler fetches that build the
+rearranged matrix, coordinate bookkeeping and the tiny per-block-pair regression.  Device side
+(libnlf_b200): every pass over the n x n matrix -- masked per-diagonal means in numpy's summation
+order, the per-block rescale, the gap-column sums and the gap-free compaction.
+
+``assembleSV`` / ``filterSV`` / ``filterAssembly`` (graph assembly of SVs) belong to the upstream
+``assemble-complexSVs`` step and are out of scope here.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .callers import Fusion
+from .scoring import DeviceAssembly
+from .util import find_chrom_pre
+
+log = logging.getLogger(__name__)
+
+__all__ = ["complexSV"]
+
+_MAXDIS_LADDER = (200000, 400000, 500000, 1000000, 1500000, 2000000)   # assembly.py:513
+
+
+class complexSV(Fusion):
+
+    def __init__(self, clr, candidate, span=5000000, col='sweight', protocol='insitu',
+                 flexible=True, slopes={}, expected_values=None):
+        self.clr = clr
+        self.res = clr.binsize
+        self.protocol = protocol
+        self.pre = find_chrom_pre(list(clr.chromnames))
+        self.span = span
+        self.flexible = flexible
+        self.slopes = slopes
+        self.balance_type = col if col in ('weight', 'sweight') else False
+        self.chroms = {c: [0, clr.chromsizes[c]] for c in clr.chromnames}
+        self._asm = None
+        self._gap_free = None
+        self._hcm = None
+        self._scale_plan = None
+
+        self.parse_input(candidate)
+        self.tb, self.to = [], []
+        last = len(self.sv_list) - 1
+        for k, sv in enumerate(self.sv_list):
+            # only the outermost ends honour the user-given bounds (assembly.py:303-318)
+            left = self.bounds[0] if k == 0 else None
+            right = self.bounds[1] if k == last else None
+            intervals, directs = self.get_single_block(sv, left_bound=left, right_bound=right)
+            self.tb.extend(intervals)
+            self.to.extend(directs)
+
+        if expected_values is None:
+            self.load_expected()
+        else:
+            self.expected = expected_values
+
+    # ------------------------------------------------------------------ parsing / geometry
+    def parse_input(self, candidate):
+        """'type,c1,p1,s1,c2,p2,s2 ... chrom,bound1 chrom,bound2' (assembly.py:323-335)."""
+        fields = candidate.split()
+        self.sv_list = []
+        for tok in fields[:-2]:
+            _, c1, p1, s1, c2, p2, s2 = tok.split(',')
+            self.sv_list.append((c1, c2, int(p1), int(p2), s1, s2))
+        b1 = fields[-2].split(',')
+        b2 = fields[-1].split(',')
+        self.bounds = [(b1[0], int(b1[1])), (b2[0], int(b2[1]))]
+
+    def _piece(self, chrom, pos, keep_left, bound):
+        """Interval retained next to a breakpoint: the side left of ``pos`` when ``keep_left``,
+        out to ``bound`` (flexible assemblies) or to +-span clipped to the chromosome."""
+        lo, hi = self.chroms[chrom]
+        if self.flexible and bound is not None:
+            return [chrom, bound[1], pos] if keep_left else [chrom, pos, bound[1]]
+        if keep_left:
+            return [chrom, max(lo, pos - self.span), pos]
+        return [chrom, pos, min(pos + self.span, hi)]
+
+    def get_single_block(self, sv, left_bound=None, right_bound=None):
+        """Two intervals and their traversal directions for one SV (assembly.py:337-385):
+        '+' at a breakpoint keeps the side left of it, '-' the side right of it; the second
+        piece is traversed 5'->3' ('+') exactly when it lies right of its breakpoint."""
+        c1, c2, p1, p2, s1, s2 = sv
+        c1, c2 = self.pre + c1, self.pre + c2
+        directions = [s1, '-' if s2 == '+' else '+']
+        intervals = [self._piece(c1, p1, s1 == '+', left_bound),
+                     self._piece(c2, p2, s2 != '-', right_bound)]
+        return intervals, directions
+
+    def get_bias(self, r):
+        col = 'weight' if self.balance_type == False else self.balance_type   # noqa: E712 (reference semantics)
+        bias = self.clr.bins().fetch(r)[col].values
+        bias = np.array(bias, dtype=np.float64, copy=True)
+        bias[np.isnan(bias)] = 0
+        return bias
+
+    def get_matrix(self, r1, r2):
+        M = self.clr.matrix(balance=self.balance_type).fetch(r1, r2)
+        if self.balance_type:
+            M[np.isnan(M)] = 0
+        return M
+
+    def reorganize_matrix(self, map_only=False):
+        """Blocks, orientations, bin index, coordinate maps and the rearranged upper-triangular
+        matrix (assembly.py:408-492).  I/O bound: (k+1)(k+2)/2 region fetches.
+
+        ``map_only=True`` builds the geometry (Map, reverse, bounds, index, chains) without
+        fetching any contact data: what the reference's second, flexible ``complexSV`` is used
+        for at scripts/neoloop-caller:210-216."""
+        tb, to = self.tb, self.to
+        blocks, orients = [tb[0]], [to[0]]
+        for i in range(1, len(tb) - 1, 2):
+            # the piece leaving SV k and the piece entering SV k+1 form one middle block
+            assert to[i] == to[i + 1]
+            assert tb[i][0] == tb[i + 1][0]
+            if to[i] == '+':
+                a, b = tb[i][1], tb[i + 1][2]
+                assert a < b
+                blocks.append([tb[i][0], a, b])
+            else:
+                a, b = tb[i][2], tb[i + 1][1]
+                assert a > b
+                blocks.append([tb[i][0], b, a])
+            orients.append(to[i])
+        blocks.append(tb[-1])
+        orients.append(to[-1])
+
+        res = self.res
+        index, Map, bounds = [], [], []
+        start = 0
+        for r, o in zip(blocks, orients):
+            nbin = self.clr.bins().fetch(tuple(r))['chrom'].size
+            index.append((start, start + nbin))
+            first = r[1] // res * res
+            coords = [(r[0], first + k * res) for k in range(nbin)]
+            ids = range(start, start + nbin)
+            lo_end, hi_end = (r[0], first), (r[0], r[2] // res * res)
+            if o == '+':
+                Map.extend(zip(coords, ids))
+                bounds += [(start, lo_end), (start + nbin - 1, hi_end)]
+            else:
+                Map.extend(zip(coords[::-1], ids))
+                bounds += [(start, hi_end), (start + nbin - 1, lo_end)]
+            start += nbin
+        forward = dict(Map)
+
+        n = index[-1][1]
+        self.Map = forward
+        self.reverse = {forward[k]: k for k in forward}
+        self.bounds = bounds
+        self.orients = orients
+        self.index = index
+        self.blocks = blocks
+        self.chains = {}
+        for k, (lo, hi) in enumerate(index):
+            for ri in range(lo, hi):
+                self.chains[ri] = k
+        self._asm = None
+        self._gap_free = None
+        self._hcm = None
+        self._n_bins = n
+        if map_only:
+            return
+        M = np.zeros((n, n))
+        bias_parts = []
+        for j1, (r1, o1, i1) in enumerate(zip(blocks, orients, index)):
+            b = self.get_bias(r1)
+            bias_parts.append(b if o1 == '+' else b[::-1])
+            for j2, (r2, o2, i2) in enumerate(zip(blocks, orients, index)):
+                if j1 > j2:
+                    continue
+                sub = self.get_matrix(r1, r2)
+                if o1 == '-':
+                    sub = sub[::-1, :]
+                if o2 == '-':
+                    sub = sub[:, ::-1]
+                M[i1[0]:i1[1], i2[0]:i2[1]] = sub
+
+        self.fusion_matrix = np.triu(M)
+        self.bias = np.concatenate(bias_parts) if bias_parts else np.r_[[]]
+
+    # ------------------------------------------------------------------ device plumbing
+    def _device_assembly(self) -> DeviceAssembly:
+        if self._asm is None:
+            self._asm = DeviceAssembly(self.fusion_matrix, self.bias, self.index, getattr(self, '_ctx', None))
+            if self._scale_plan is not None:
+                self._asm.set_scales(*self._scale_plan)
+        return self._asm
+
+    # ------------------------------------------------------------------ normalisation
+    def correct_heterozygosity(self):
+        """Per-block-pair slopes against the global expected and the rescaled matrix
+        (assembly.py:495-571).  GPU: masked diagonal means (once, to 2 Mb: the reference's six
+        maxdis values are prefixes of it), rescale, symmetrise/triu.  Host: the regressions."""
+        asm = self._device_assembly()
+        nb = len(self.blocks)
+        res = self.res
+        maxdiag = _MAXDIS_LADDER[-1] // res
+        mean, _cnt = asm.diag_means(maxdiag, mink=3)
+
+        slopes, exps, pair_binary = {}, {}, {}
+        p = 0
+        for j1 in range(nb):
+            for j2 in range(j1, nb):
+                row = mean[p]
+                p += 1
+                kept = np.where(~np.isnan(row))[0]
+                rs, ss, ws = [], [], []
+                memo = {}
+                local_exp = {}
+                for maxdis in _MAXDIS_LADDER:
+                    upto = kept[kept <= maxdis // res]
+                    local_exp = {int(i): row[i] for i in upto}
+                    key = len(upto)                      # prefixes: same length <=> same dictionary
+                    if key not in memo:
+                        memo[key] = self.linear_regression(local_exp, self.expected, min_samples=5)
+                    r, s, w = memo[key]
+                    rs.append(r)
+                    ss.append(s)
+                    ws.append(w)
+                rs = np.r_[rs]
+                r = rs.max()
+                s = ss[rs.argmax()]
+                if any(ws):
+                    pair_binary[(j1, j2)] = 1 if (r > 0.6 and s > 0) else 0
+                else:
+                    pair_binary[(j1, j2)] = 1
+                slopes[(j1, j2)] = [r, s]
+                exps[(j1, j2)] = local_exp
+
+        op = np.zeros((nb, nb), dtype=np.int32)
+        val = np.ones((nb, nb), dtype=np.float64)
+        for j1 in range(nb):
+            for j2 in range(j1, nb):
+                ms = max(slopes[(j1, j1)][1], slopes[(j2, j2)][1])
+                if (j1, j2) in self.slopes:
+                    op[j1, j2], val[j1, j2] = 1, self.slopes[(j1, j2)]
+                elif slopes[(j1, j2)][0] > 0.6 and slopes[(j1, j2)][1] > 0 and ms > 0:
+                    if j1 == j2:
+                        op[j1, j2], val[j1, j2] = 1, slopes[(j1, j2)][1]
+                    else:
+                        op[j1, j2], val[j1, j2] = 2, min(1 / slopes[(j1, j2)][1], 5 / ms)
+        self._scale_plan = (op, val)
+        asm.set_scales(op, val)
+        self._hcm = None
+        self._gap_free = None
+
+        self.slopes_ = slopes
+        self.exps = exps
+        self.pair_binary = pair_binary
+        self.valid_counts = sum(pair_binary.values())
+        table = np.zeros((nb, nb))
+        for (i, j), (r, _s) in slopes.items():
+            if r > 0.6:
+                table[i, j] = table[j, i] = 1
+        self.connectivity = all(not np.any(table.diagonal(i) == 0) for i in range(1, min(nb, 3)))
+
+    @property
+    def hcm(self):
+        """Heterozygosity-corrected upper-triangular matrix (assembly.py:557)."""
+        if self._hcm is None:
+            self._hcm = self._device_assembly().hcm()
+        return self._hcm
+
+    @property
+    def symm_hcm(self):
+        h = self.hcm.copy()
+        x, y = h.nonzero()
+        h[y, x] = h[x, y]
+        return h
+
+    # ------------------------------------------------------------------ coordinates
+    def index_to_coordinates(self, loop_list):
+        """Gap-free indices -> {(c1, s1, e1, c2, s2, e2): [distance on the assembly, neo flag]}
+        (assembly.py:574-596)."""
+        lines = {}
+        res = self.res
+        for i, j, _v in loop_list:
+            x, y = self.index_map[i], self.index_map[j]
+            a, b = self.reverse[x], self.reverse[y]
+            if a > b:
+                a, b = b, a
+            key = (a[0], a[1], a[1] + res, b[0], b[1], b[1] + res)
+            lines[key] = [(y - x) * res, 0 if self.chains[x] == self.chains[y] else 1]
+        return lines

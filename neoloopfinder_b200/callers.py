@@ -1,0 +1,351 @@
+"""Drop-in for the scoring classes of ``neoloop/callers.py`` on the neoloop-caller path.
+
+Same class names, constructor/method signatures, attribute names and error behaviour as the
+reference; every pass over matrix data runs in the CUDA library
+(``libnlf_b200.so``) through ``scoring.py``.  Host-only pieces are the ones the survey leaves on
+the host: the per-block-pair regression (Spearman + isotonic + Huber on <= 400 points) and
+dictionary/coordinate bookkeeping.
+
+Not provided (off the neoloop-caller path): ``Fusion.get_matrix``,
+``detect_bounds``, ``allele_slope``, ``extract_bias`` (used only by assemble-complexSVs).
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from .forest import DeviceForest, load_forest
+from .scoring import DeviceAssembly, ScoreBatch, local_clustering_gpu, pool_buckets
+
+log = logging.getLogger(__name__)
+
+__all__ = ["check_increasing", "clean_inputs", "Fusion", "Peakachu", "combine_annotations"]
+
+
+def check_increasing(x, y):
+    """(warning, increasing) from the sign of Spearman's rho and its Fisher 95 % interval
+    (neoloop/callers.py:19-63)."""
+    from scipy.stats import spearmanr
+    rho, _ = spearmanr(x, y)
+    warning = False
+    increasing = rho >= 0
+    if rho not in (-1.0, 1.0) and len(x) > 3:
+        F = 0.5 * math.log((1.0 + rho) / (1.0 - rho))
+        se = 1 / math.sqrt(len(x) - 3)
+        lo, hi = math.tanh(F - 1.96 * se), math.tanh(F + 1.96 * se)
+        if np.sign(lo) != np.sign(hi):
+            warning = True
+    return warning, increasing
+
+
+def clean_inputs(Xi, X, Y, increasing_bool):
+    """Drop a noisy head of the curve located with an isotonic fit (neoloop/callers.py:65-89)."""
+    from sklearn.isotonic import IsotonicRegression
+    fit = IsotonicRegression(increasing=increasing_bool).fit(Xi, Y).predict(Xi)
+    vi = np.where(np.diff(fit) < 0)[0]
+    runs = np.split(vi, np.where(np.diff(vi) != 1)[0] + 1)
+    si = 0
+    for k in range(len(runs) - 1):
+        cur, nxt = runs[k], runs[k + 1]
+        if cur.size / (nxt[0] - cur[0]) > 0.5:
+            si = cur[0]
+            break
+    if si / X.size > 0.3:
+        si = vi[0]
+        if si / X.size > 0.3:
+            si = 0
+    return X[si:], Y[si:]
+
+
+class Fusion(object):
+    """The part of the reference's ``Fusion`` that the neoloop-caller path inherits."""
+
+    def load_expected(self):
+        """Bundled GM12878 in-situ expected tables (neoloop/callers.py:120-134)."""
+        import joblib
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+        name = {5000: "5k", 10000: "10k", 20000: "20k", 25000: "25k", 40000: "40k", 50000: "50k"}.get(self.res)
+        self.expected = {}
+        path = os.path.join(here, f"gm.insitu.expected.{name}.pkl") if name else None
+        if path and os.path.exists(path):
+            self.expected = joblib.load(path)
+
+    def linear_regression(self, exp1, exp2, min_samples=5):
+        """Slope of local vs global expected with a Huber fit (neoloop/callers.py:370-412)."""
+        from sklearn.linear_model import HuberRegressor
+        keys = [i for i in sorted(exp1) if i in exp2]
+        Xi = np.r_[keys]
+        X = np.r_[[exp2[i] for i in keys]]
+        Y = np.r_[[exp1[i] for i in keys]]
+        if X.size < min_samples:
+            return 0, 0, False
+        warning, increasing = check_increasing(Xi, Y)
+        Xc, Yc = clean_inputs(Xi, X, Y, increasing)
+        rscores, slopes = [], []
+        for X_, Y_ in ((X, Y), (Xc, Yc)):
+            X2 = X_[:, np.newaxis]
+            huber = HuberRegressor().fit(X2, Y_)
+            inliers = np.logical_not(huber.outliers_)
+            if inliers.sum() < min_samples:
+                r, s = 0, 0
+            else:
+                r = huber.score(X2[inliers], Y_[inliers])
+                s = huber.coef_[0]
+            rscores.append(r)
+            slopes.append(s)
+        rscores = np.r_[rscores]
+        slopes = np.r_[slopes]
+        return rscores.max(), slopes[np.argmax(rscores)], warning
+
+    def remove_gaps(self):
+        """Gap-free matrix and gap-free -> original index map (neoloop/callers.py:504-522).
+        The column sums and the compaction run on the GPU; ``gap_free`` is materialised on the
+        host only if somebody reads the attribute."""
+        asm = self._device_assembly()
+        kept = asm.kept_index()
+        self.index_map = dict(zip(np.arange(len(kept)), kept.astype(np.int64)))
+        self._gap_free = None
+
+    @property
+    def gap_free(self):
+        if getattr(self, "_gap_free", None) is None:
+            self._gap_free = _DeviceBackedMatrix(self._device_assembly())
+        return self._gap_free
+
+
+class _DeviceBackedMatrix:
+    """Lazy stand-in for the gap-free ndarray: remembers the device assembly it came from, so
+    ``Peakachu(fu.gap_free, ...)`` scores straight from HBM; any other consumer that treats it as
+    an array (np.asarray, indexing, .sum() ...) triggers one device-to-host copy."""
+
+    def __init__(self, asm):
+        self._nlf_assembly = asm
+        self._host = None
+        n = len(asm.kept_index())
+        self.shape = (n, n)
+        self.ndim = 2
+        self.dtype = np.dtype(np.float64)
+
+    def _materialise(self):
+        if self._host is None:
+            self._host = self._nlf_assembly.gap_free()
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._materialise()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        return self._materialise()[key]
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self._materialise(), name)
+
+
+class Peakachu():
+    """Loop scoring of one gap-free matrix (neoloop/callers.py:525-831) on the GPU."""
+
+    def __init__(self, matrix, upper=4000000, res=10000, protocol='insitu'):
+        self.w = 7
+        self.r = res
+        self.protocol = protocol
+        self._upper = upper // res
+        self._ctx = _lib.Context.get()
+        self._batch = ScoreBatch(4, self._upper, self._ctx)
+        asm = getattr(matrix, "_nlf_assembly", None)
+        if asm is not None:
+            self._job = self._batch.add_assembly(asm)
+            self._matrix = matrix
+        else:
+            self._matrix = np.ascontiguousarray(np.asarray(matrix), dtype=np.float64)
+            self._job = self._batch.add_dense(self._matrix)
+        self._shape = (self._batch.n[self._job],) * 2
+        self._cand = None
+        self._M = None
+        self.model_path = None
+        self._forest = None
+        self._model = None
+        self.exp_arr = None
+        self._scored_thre = None
+        # the reference's constructor fails here when no diagonal is longer than 5 bins
+        # (IsotonicRegression.fit on an empty sample raises ValueError, callers.py:544-551)
+        try:
+            self._batch.counts()
+        except _lib.NLFError as exc:
+            if exc.code == _lib.NLF_ERR_EMPTY_FIT:
+                raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required "
+                                 "by IsotonicRegression (matrix has no diagonal longer than 5 bins)") from exc
+            raise
+
+    # -- attributes of the reference object -------------------------------------------------
+    @property
+    def M(self):
+        """CSR matrix of the finite band (callers.py:531-535); built on the host on demand."""
+        if self._M is None:
+            from scipy import sparse
+            m = np.asarray(self._matrix)
+            R, Cc = m.nonzero()
+            data = m[R, Cc]
+            ok = np.isfinite(data) & (Cc - R > -14) & (Cc - R < self._upper + 14)
+            self._M = sparse.csr_matrix((data[ok], (R[ok], Cc[ok])), shape=m.shape)
+        return self._M
+
+    def _candidates(self):
+        if self._cand is None:
+            r, c = self._batch.candidates(self._job)
+            self._cand = (r.astype(np.int64), c.astype(np.int64))
+        return self._cand
+
+    @property
+    def ridx(self):
+        return self._candidates()[0]
+
+    @property
+    def cidx(self):
+        return self._candidates()[1]
+
+    @property
+    def model(self):
+        if self._model is None and self.model_path is not None:
+            import joblib
+            self._model = joblib.load(self.model_path)
+        return self._model
+
+    # -- reference methods -------------------------------------------------------------------
+    def get_candidates(self, lower, upper):
+        """Kept for API compatibility: candidates are computed on the GPU for the (4, upper)
+        range fixed by the constructor (callers.py:536)."""
+        if lower != 4 or upper != self._upper:
+            raise ValueError("neoloopfinder_b200 computes candidates for lower=4 and the constructor's upper")
+        self._cand = None
+        self._candidates()
+
+    def load_models(self, model_fil_path):
+        """callers.py:572-577, but the forest is flattened once per file and kept on the GPU."""
+        if isinstance(model_fil_path, DeviceForest):
+            self._forest = model_fil_path
+        else:
+            self.model_path = model_fil_path
+            self._forest = load_forest(model_fil_path, self._ctx)
+        self.w = self._forest.w
+
+    def load_expected(self, expected_values):
+        self.exp_arr = np.r_[[expected_values[i] for i in sorted(expected_values)]]
+
+    def getwindow(self, coords, w):
+        """Features (float64, rows x (2w+1)^2) and coordinates of the windows that pass the
+        reference's masks (callers.py:583-612)."""
+        if len(coords) < 2:
+            return [], []
+        coords = np.r_[coords]
+        fea, clist = self._batch.getwindow(self._job, coords[:, 0], coords[:, 1], w, self.exp_arr)
+        if len(fea) == 0 and self._n_inside(coords, w) < 2:
+            return [], []
+        return fea, clist.astype(np.int64)
+
+    def _n_inside(self, coords, w):
+        xi, yi = coords[:, 0], coords[:, 1]
+        return int(((xi - w >= 0) & (yi + w + 1 <= self._shape[0]) & (yi - xi - 2 >= w)).sum())
+
+    def _score(self, thre):
+        if self._forest is None or self.exp_arr is None:
+            raise RuntimeError("call load_expected() and load_models() before predict()")
+        if self._scored_thre is None:
+            self._batch.score(self._forest, self.exp_arr, thre, self.w)
+            self._scored_thre = thre
+        elif self._scored_thre != thre:
+            # one batch is scored once; a different threshold needs a fresh pass
+            old = self._batch
+            self._batch = ScoreBatch(4, self._upper, self._ctx)
+            asm = getattr(self._matrix, "_nlf_assembly", None)
+            self._job = self._batch.add_assembly(asm) if asm is not None else self._batch.add_dense(np.asarray(self._matrix))
+            old.close()
+            self._batch.score(self._forest, self.exp_arr, thre, self.w)
+            self._scored_thre = thre
+
+    def predict(self, thre, no_pool=False, min_count=2, index_map=None, chains=None):
+        """[(i, j, probability)] of the called loops (callers.py:614-639)."""
+        self._score(thre)
+        n_cand, n_scored, n_don = self._batch.counts()
+        if n_scored[self._job] < 2:
+            return []
+        di, dj, dp, dv = self._batch.donuts(self._job)
+        Donuts = {(int(a), int(b)): v for a, b, v in zip(di, dj, dv)}
+        prob = {(int(a), int(b)): float(q) for a, b, q in zip(di, dj, dp)}
+        if not no_pool:
+            keep = self.local_clustering(Donuts, min_count=min_count, index_map=index_map, chains=chains)
+        else:
+            keep = Donuts
+        return [(i, j, prob[(i, j)]) for i, j in keep]
+
+    def scored_pixels(self):
+        """(clist, probas) of the last predict(): every scored window in candidate order."""
+        i, j, p = self._batch.scored(self._job)
+        return np.stack([i, j], 1).astype(np.int64), p
+
+    def local_clustering(self, Donuts, min_count=2, r=15000, index_map=None, chains=None):
+        """Pool thresholded pixels per (chain, chain) region (callers.py:668-697)."""
+        if not len(Donuts):
+            return set()
+        ij = np.array(list(Donuts), dtype=np.int64).reshape(-1, 2)
+        val = np.array([Donuts[(i, j)] for i, j in ij], dtype=np.float64)
+        if chains is None:
+            ci = cj = None
+        else:
+            if index_map is None:
+                xs, ys = ij[:, 0], ij[:, 1]
+            else:
+                xs = np.array([index_map[i] for i in ij[:, 0]])
+                ys = np.array([index_map[j] for j in ij[:, 1]])
+            ci = np.array([chains[x] for x in xs])
+            cj = np.array([chains[y] for y in ys])
+        return local_clustering_gpu(ij, val, self.r, min_count, r, ci, cj, self._ctx)
+
+    def _local_clustering(self, Donuts, min_count=1, r=15000):
+        """One region (callers.py:699-738) -> list of kept (i, j)."""
+        if not len(Donuts):
+            return []
+        ij = np.array(list(Donuts), dtype=np.int64).reshape(-1, 2)
+        val = np.array([Donuts[(i, j)] for i, j in ij], dtype=np.float64)
+        mask = pool_buckets([(ij[:, 0], ij[:, 1], val)], self.r, min_count, r, self._ctx)[0]
+        return [(int(a), int(b)) for a, b in ij[mask]]
+
+    def close(self):
+        self._batch.close()
+
+
+def combine_annotations(byres):
+    """Merge loop calls of several resolutions, finest first: a coarser loop is dropped when a
+    finer call falls inside its two bins, and its labels go to those finer calls
+    (neoloop/callers.py:834-868).  Returns sorted rows [c1, s1, e1, c2, s2, e2, label]."""
+    levels = sorted(byres)
+    pool = byres[levels[0]]
+    seen = [levels[0]]
+    for res in levels[1:]:
+        current = byres[res]
+        for loop in current:
+            for pr in seen:
+                hits = 0
+                for i in range(loop[1] // pr, loop[2] // pr + 1):
+                    for j in range(loop[4] // pr, loop[5] // pr + 1):
+                        key = (loop[0], i * pr, i * pr + pr, loop[3], j * pr, j * pr + pr)
+                        if key in pool:
+                            hits += 1
+                            pool[key].extend(current[loop])
+                if hits == 0:
+                    pool[loop] = current[loop]
+        seen.append(res)
+    rows = []
+    for key in sorted(pool):
+        labels = [",".join([t[0], str(t[1]), str(t[2])]) for t in set(pool[key])]
+        rows.append(list(map(str, key)) + [",".join(labels)])
+    return rows

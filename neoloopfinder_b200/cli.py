@@ -1,0 +1,370 @@
+"""``neoloop-caller`` on B200: same flags, same outputs (scripts/neoloop-caller of the reference).
+
+What changes underneath:
+* every assembly of a resolution is normalised and scored through the CUDA library, all assemblies
+  of one GPU in ONE batch (``call_assemblies``); ``pipeline()`` keeps the reference's
+  one-assembly signature (scripts/neoloop-caller:185-218) for drop-in use;
+* the work is sharded over the visible GPUs by assembly (greedy longest-processing-time on the
+  estimated pixel count); ``--nproc`` keeps its meaning for the CPU-side prologue;
+* the model lookup bug of the reference (scripts/neoloop-caller:245 indexes the platform-keyed
+  table with a resolution) is fixed to ``links[platform]``; without network the model file must
+  already sit in ``--cachefolder`` under the reference's cache name
+  ``peakachu_v2.res{R}.depth{D}.pkl`` (or be given with ``--model``);
+* contact maps are opened with ``coolshim.load_cooler`` (.json synthetic spec, .npz arrays, or a
+  real cooler URI when the ``cooler`` package exists).
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import logging.handlers
+import os
+import sys
+import threading
+import traceback
+from typing import Dict, List, Optional
+
+import numpy as np
+
+__version__ = "0.5.0+b200.1"
+
+log = logging.getLogger(__name__)
+
+
+# ----------------------------------------------------------------------------------------------
+# scoring of assemblies
+# ----------------------------------------------------------------------------------------------
+def estimate_pixels(n_bins: int) -> int:
+    """Upper bound of scored pixels for a gap-free matrix of n bins."""
+    return max(0, 393 * n_bins - 80172) if n_bins >= 401 else max(0, n_bins * (n_bins - 8) // 2)
+
+
+def lpt_shards(weights: List[float], n_shards: int) -> List[List[int]]:
+    """Greedy longest-processing-time partition of item indices into n_shards lists."""
+    order = sorted(range(len(weights)), key=lambda k: (-weights[k], k))
+    loads = [0.0] * n_shards
+    shards = [[] for _ in range(n_shards)]
+    for k in order:
+        s = min(range(n_shards), key=lambda q: (loads[q], q))
+        shards[s].append(k)
+        loads[s] += weights[k]
+    return shards
+
+
+def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model, expected, ctx=None,
+                    stats=None):
+    """pipeline() for many assemblies on one GPU, batched.  Returns {ID: final_dict or None}."""
+    from . import _lib
+    from .assembly import complexSV
+    from .forest import DeviceForest, load_forest
+    from .scoring import ScoreBatch, pool_buckets
+
+    ctx = ctx or _lib.Context.get()
+    forest = model if isinstance(model, DeviceForest) else load_forest(model, ctx)
+    res = clr.binsize
+    out = {}
+    live = []
+    for ID in ids:
+        fu = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu',
+                       expected_values=expected, flexible=False)
+        fu.reorganize_matrix()
+        if len(fu.Map) != fu.fusion_matrix.shape[0]:
+            out[ID] = None                         # invalid assembly (scripts/neoloop-caller:196-197)
+            continue
+        fu._ctx = ctx
+        fu.correct_heterozygosity()
+        fu.remove_gaps()
+        live.append((ID, fu))
+    if not live:
+        return out
+    exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
+    batch = ScoreBatch(4, 400 * res // res, ctx)
+    for _ID, fu in live:
+        batch.add_assembly(fu._device_assembly())
+    batch.score(forest, exp_arr, prob, forest.w)
+    n_cand, n_scored, n_don = batch.counts()
+    if stats is not None:
+        stats["candidates"] = stats.get("candidates", 0) + int(n_cand.sum())
+        stats["scored"] = stats.get("scored", 0) + int(n_scored.sum())
+        stats["donuts"] = stats.get("donuts", 0) + int(n_don.sum())
+
+    # Donuts of every assembly, bucketed by (assembly, chain_i, chain_j) for one pooling launch
+    donuts = []
+    buckets, owners = [], []
+    for job, (ID, fu) in enumerate(live):
+        if n_scored[job] < 2:                      # callers.py:619-620
+            donuts.append(None)
+            continue
+        di, dj, dp, dv = batch.donuts(job)
+        donuts.append((di, dj, dp, dv))
+        if nopool or len(di) == 0:
+            continue
+        kept = fu._device_assembly().kept_index()
+        chain_of = np.array([fu.chains[k] for k in range(fu.fusion_matrix.shape[0])])
+        ci, cj = chain_of[kept[di]], chain_of[kept[dj]]
+        key = ci.astype(np.int64) * (1 << 24) + cj
+        for kk in np.unique(key):
+            sel = np.where(key == kk)[0]
+            buckets.append((di[sel], dj[sel], dv[sel]))
+            owners.append((job, sel))
+    masks = pool_buckets(buckets, res, mmp, 15000, ctx) if buckets else []
+    keep_by_job = {}
+    for (job, sel), m in zip(owners, masks):
+        keep_by_job.setdefault(job, []).append(sel[m])
+
+    for job, (ID, fu) in enumerate(live):
+        d = donuts[job]
+        if d is None:
+            loop_index = []
+        else:
+            di, dj, dp, dv = d
+            if nopool:
+                sel = np.arange(len(di))
+            else:
+                parts = keep_by_job.get(job, [])
+                sel = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+            loop_index = [(int(di[k]), int(dj[k]), float(dp[k])) for k in sel]
+        loops = fu.index_to_coordinates(loop_index)
+        # keep calls inside the ORIGINAL (flexible) assembly only; geometry without re-fetching
+        fu2 = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu', expected_values=expected)
+        fu2.reorganize_matrix(map_only=True)
+        out[ID] = {k: (ID, v[0], v[1]) for k, v in loops.items()
+                   if (k[0], k[1]) in fu2.Map and (k[3], k[4]) in fu2.Map}
+        fu._device_assembly().close()
+    batch.close()
+    return out
+
+
+def pipeline(clr, index, assemblies, rsize, balance, prob, mmp, nopool, models_by_res, expected):
+    """One assembly, the reference's signature (scripts/neoloop-caller:185-218)."""
+    res = clr.binsize
+    return call_assemblies(clr, [index], assemblies, rsize, balance, prob, mmp, nopool, models_by_res[res],
+                           expected)[index]
+
+
+def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, nopool, model_path, expected,
+                    devices: Optional[List[int]] = None, stats=None):
+    """All assemblies of one resolution, sharded over GPUs by assembly (no collective: the
+    per-assembly results are KB-sized dictionaries merged on the host)."""
+    from . import _lib
+    if devices is None:
+        devices = list(range(_lib.device_count()))
+    if not devices:
+        raise RuntimeError("no CUDA device visible: neoloopfinder_b200 has no CPU fallback")
+    ids = list(assemblies)
+    res = clr.binsize
+    # cost estimate from the assembly geometry only
+    weights = []
+    for ID in ids:
+        nsv = max(1, len(assemblies[ID].split()) - 2)
+        weights.append(float(estimate_pixels(int((2 + 0.5 * (nsv - 1)) * rsize // res))))
+    shards = lpt_shards(weights, len(devices))
+    results: Dict[str, Optional[dict]] = {}
+    errors = []
+
+    def work(dev, idx):
+        try:
+            ctx = _lib.Context.get(dev)
+            st = {} if stats is not None else None
+            r = call_assemblies(clr, [ids[k] for k in idx], assemblies, rsize, balance, prob, mmp, nopool,
+                                model_path, expected, ctx, st)
+            results.update(r)
+            if stats is not None:
+                for k, v in st.items():
+                    stats[k] = stats.get(k, 0) + v
+        except BaseException as exc:      # noqa: BLE001 - re-raised in the caller thread
+            errors.append(exc)
+
+    if len(devices) == 1:
+        work(devices[0], shards[0])
+    else:
+        threads = [threading.Thread(target=work, args=(d, s)) for d, s in zip(devices, shards) if s]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    return [results[ID] for ID in ids]
+
+
+def merge_results(results):
+    """scripts/neoloop-caller:161-170."""
+    cache = {}
+    for tmp in results:
+        if tmp is None:
+            continue
+        for key in tmp:
+            cache.setdefault(key, []).append(tmp[key])
+    return cache
+
+
+# ----------------------------------------------------------------------------------------------
+# model lookup (scripts/neoloop-caller:220-270, fixed and offline-aware)
+# ----------------------------------------------------------------------------------------------
+def match_digital_values(arr, v):
+    arr = list(arr)
+    return arr[int(np.argmin(np.abs(v - np.r_[arr])))]
+
+
+def locate_peakachu_models(cachefolder, clrs_by_res, platform='Hi-C'):
+    """{res: model path}.  Picks the model whose resolution and intra-chromosomal depth are
+    nearest, as the reference does (with the platform lookup fixed), then expects the file in the
+    cache folder under the reference's cache name (no network in this build)."""
+    from .model_table import model_table
+    table = model_table(platform)
+    out = {}
+    for res, clr in clrs_by_res.items():
+        m_res = match_digital_values(table, res)
+        info = clr.info
+        if 'sum' in info:
+            depth = info['sum']
+        elif info['nnz'] < 100000000:
+            depth = clr.pixels()[:]['count'].values.sum()
+        else:
+            depth = info['nnz'] * 2.14447683
+        depth = 3031042417 / clr.chromsizes.sum() * depth
+        depth = res / m_res * depth
+        intra = depth * 0.73256754
+        m_depth = match_digital_values(table[m_res], intra)
+        path = os.path.join(cachefolder, table[m_res][m_depth])
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found. This build has no network access: place the Peakachu model "
+                f"({platform}, {m_res} bp, depth {m_depth}) there or pass --model.")
+        out[res] = path
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# command line
+# ----------------------------------------------------------------------------------------------
+def getargs(argv=None):
+    parser = argparse.ArgumentParser(description='''Identify novel loop interactions across SV
+                                     points.''', formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('-v', '--version', action='version', version=' '.join(['%(prog)s', __version__]),
+                        help='Print version number and exit.')
+    parser.add_argument('-O', '--output', help='Path to the output file.')
+    parser.add_argument('-H', '--hic', nargs='+', help='''List of cooler URIs. If URIs at multiple
+                        resolutions are provided, the program will first detect neo-loops from
+                        each individual resolution, and then combine results from all resolutions
+                        in a non-redundant way. If an interaction is detected as a loop in multiple
+                        resolutions, only the one with the highest resolution will be recorded.''')
+    parser.add_argument('--assembly', help='''The assembled SV list outputed by assemble-complexSVs.''')
+    parser.add_argument('--cachefolder', default='.cache', help='''Path to a folder to place the pre-trained
+                        Peakachu models.''')
+    parser.add_argument('-R', '--region-size', default=3000000, type=int,
+                        help='''The extended genomic span of SV break points.(bp)''')
+    parser.add_argument('--balance-type', default='CNV', choices=['CNV', 'ICE', 'RAW'], help='Normalization method.')
+    parser.add_argument('--platform', default='Hi-C',
+                        choices=['Hi-C', 'CTCF-ChIAPET', 'Pol2-ChIAPET', 'H3K27ac-HiChIP', 'H3K4me3-HiChIP',
+                                 'CTCF-HiChIP', 'SMC1A-HiChIP', 'HiCAR', 'TrAC-loop'],
+                        help='''Name of the experimental platform you used to generate your chromatin contact data.''')
+    parser.add_argument('--prob', type=float, default=0.9, help='Probability threshold.')
+    parser.add_argument('--no-clustering', action='store_true', help='No pooling will be performed if specified.')
+    parser.add_argument('--min-marginal-peaks', type=int, default=2,
+                        help='''Minimum marginal number of loops when detecting loop anchors.''')
+    parser.add_argument('--nproc', default=1, type=int, help='Number of worker processes.')
+    parser.add_argument('--logFile', default='neoloop.log', help='''Logging file name.''')
+    # additions of this build (all optional)
+    parser.add_argument('--model', nargs='+', default=None,
+                        help='''Model pickle(s), one per -H matrix in the same order; overrides the cache lookup.''')
+    parser.add_argument('--gpus', default=None,
+                        help='''Comma-separated CUDA device indices (default: every visible device).''')
+    commands = list(sys.argv[1:] if argv is None else argv)
+    if not commands:
+        commands.append('-h')
+    return parser.parse_args(commands), commands
+
+
+def run(argv=None):
+    args, commands = getargs(argv)
+    if commands[0] in ['-h', '-v', '--help', '--version']:
+        return
+    logger = logging.getLogger()
+    logger.setLevel(10)
+    console = logging.StreamHandler()
+    filehandler = logging.handlers.RotatingFileHandler(args.logFile, maxBytes=100000, backupCount=5)
+    console.setLevel('INFO')
+    filehandler.setLevel('INFO')
+    formatter = logging.Formatter(fmt='%(name)-25s %(levelname)-7s @ %(asctime)s: %(message)s',
+                                  datefmt='%m/%d/%y %H:%M:%S')
+    console.setFormatter(formatter)
+    filehandler.setFormatter(formatter)
+    logger.addHandler(console)
+    logger.addHandler(filehandler)
+    arglist = ['# ARGUMENT LIST:',
+               '# Output Path = {0}'.format(args.output),
+               '# Cache Folder = {0}'.format(args.cachefolder),
+               '# SV assembly = {0}'.format(args.assembly),
+               '# Cooler List = {0}'.format(args.hic),
+               '# Extended Genomic Span = {0}bp'.format(args.region_size),
+               '# Balance Type = {0}'.format(args.balance_type),
+               '# Probability threshold = {0}'.format(args.prob),
+               '# No pooling = {0}'.format(args.no_clustering),
+               '# Minimum marginal peaks = {0}'.format(args.min_marginal_peaks),
+               '# Number of Processes = {0}'.format(args.nproc),
+               '# Log file name = {0}'.format(args.logFile)]
+    logger.info('\n' + '\n'.join(arglist))
+
+    from .callers import combine_annotations
+    from .coolshim import load_cooler
+    from .util import autosomes, calculate_expected
+
+    balance = {'CNV': 'sweight', 'ICE': 'weight', 'RAW': False}[args.balance_type]
+    try:
+        clrs = {}
+        order = []
+        for path in args.hic:
+            lib = load_cooler(path)
+            clrs[lib.binsize] = lib
+            order.append(lib.binsize)
+        cachefolder = os.path.abspath(os.path.expanduser(args.cachefolder))
+        os.makedirs(cachefolder, exist_ok=True)
+        if args.model:
+            if len(args.model) != len(order):
+                raise ValueError('--model needs one path per -H matrix')
+            models_by_res = dict(zip(order, args.model))
+        else:
+            models_by_res = locate_peakachu_models(cachefolder, clrs, args.platform)
+        devices = None if args.gpus is None else [int(t) for t in args.gpus.split(',')]
+
+        logger.info('Load assembled SVs')
+        lines = {}
+        with open(args.assembly, 'r') as source:
+            for line in source:
+                parse = line.rstrip().split()
+                if parse:
+                    lines[parse[0]] = '\t'.join(parse[1:])
+
+        byres = {}
+        for res in sorted(clrs, reverse=True):
+            logger.info('Current resolution: {0}'.format(res))
+            clr = clrs[res]
+            logger.info('Calculate the global average contact frequencies at each genomic distance ...')
+            expected = calculate_expected(clr, autosomes(clr.chromnames), maxdis=5000000, balance=balance,
+                                          nproc=args.nproc)
+            logger.info('Done')
+            stats = {}
+            results = call_resolution(clr, lines, args.region_size, balance, args.prob, args.min_marginal_peaks,
+                                      args.no_clustering, models_by_res[res], expected, devices, stats)
+            logger.info('Scored {0} pixels ({1} candidates, {2} above the threshold)'.format(
+                stats.get('scored', 0), stats.get('candidates', 0), stats.get('donuts', 0)))
+            logger.info('Merge loops across assemblies ...')
+            byres[res] = merge_results(results)
+
+        if len(clrs) > 1:
+            logger.info('Combine loops from multiple resolutions')
+        loop_list = combine_annotations(byres)
+        logger.info('Output ...')
+        with open(args.output, 'w') as out:
+            for line in loop_list:
+                out.write('\t'.join(line) + '\n')
+        logging.info('Done')
+    except:  # noqa: E722 - same contract as the reference: traceback to the log file, exit code 1
+        traceback.print_exc(file=open(args.logFile, 'a'))
+        sys.exit(1)
+
+
+if __name__ == '__main__':
+    run()
