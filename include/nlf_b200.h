@@ -51,6 +51,10 @@ int nlf_launch_count(nlf_ctx *ctx, long long *count);
 int nlf_profile_enable(nlf_ctx *ctx, int on);
 int nlf_profile_read(nlf_ctx *ctx, int which, float *total_ms, long long *launches);
 int nlf_profile_reset(nlf_ctx *ctx);
+/* Measurement helpers: evict L2 between timed iterations; fp64 add/mul issue rate (G op/s,
+ * no FMA) measured on this device, the roofline denominator of the feature kernel. */
+int nlf_l2_flush(nlf_ctx *ctx);
+int nlf_fp64_peak(nlf_ctx *ctx, double *gops);
 
 /* ---- forest: replaces Peakachu.load_models + model.predict_proba
  *      (neoloop/callers.py:572-577, 622; sklearn _forest.py predict_proba, _tree.pyx _apply_dense).
@@ -127,6 +131,8 @@ int nlf_batch_fetch_features32(nlf_batch *b, int job, long long cap, float *fea)
 int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const int *yi, long long nc, int w,
                         const double *expected, int nexp, const double *gw, int radius,
                         double *fea, int *clist, long long *n_rows);
+/* Drop the results but keep the matrices resident, so nlf_batch_score can run again. */
+int nlf_batch_reset(nlf_batch *b);
 int nlf_batch_njobs(nlf_batch *b);
 int nlf_batch_destroy(nlf_batch *b);
 

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "nlf_profile_enable": (C.c_int, [vp, C.c_int]),
     "nlf_profile_read": (C.c_int, [vp, C.c_int, fp, llp]),
     "nlf_profile_reset": (C.c_int, [vp]),
+    "nlf_l2_flush": (C.c_int, [vp]),
+    "nlf_fp64_peak": (C.c_int, [vp, dp]),
     "nlf_forest_create": (C.c_int, [vp, C.c_int, i64p, ip, ip, ip, dp, u8p, dp, C.c_int, C.POINTER(vp)]),
     "nlf_forest_destroy": (C.c_int, [vp]),
     "nlf_forest_predict": (C.c_int, [vp, fp, C.c_longlong, dp]),
@@ -64,6 +66,7 @@ _SIGNATURES = {
     "nlf_batch_fetch_candidates": (C.c_int, [vp, C.c_int, C.c_longlong, ip, ip]),
     "nlf_batch_fetch_features32": (C.c_int, [vp, C.c_int, C.c_longlong, fp]),
     "nlf_batch_getwindow": (C.c_int, [vp, C.c_int, ip, ip, C.c_longlong, C.c_int, dp, C.c_int, dp, C.c_int, dp, ip, llp]),
+    "nlf_batch_reset": (C.c_int, [vp]),
     "nlf_batch_njobs": (C.c_int, [vp]),
     "nlf_batch_destroy": (C.c_int, [vp]),
     "nlf_pool": (C.c_int, [vp, C.c_int, i64p, ip, ip, dp, C.c_int, C.c_int, C.c_int, ip, i64p, ip, i64p, u8p]),
@@ -156,6 +159,14 @@ class Context:
         n = C.c_longlong(0)
         check(load().nlf_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def l2_flush(self):
+        check(load().nlf_l2_flush(self.h))
+
+    def fp64_peak_gops(self) -> float:
+        g = C.c_double(0)
+        check(load().nlf_fp64_peak(self.h, C.byref(g)))
+        return g.value
 
     def profile(self, on=True):
         check(load().nlf_profile_enable(self.h, 1 if on else 0))

@@ -57,7 +57,7 @@ def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, mod
     from . import _lib
     from .assembly import complexSV
     from .forest import DeviceForest, load_forest
-    from .scoring import ScoreBatch, pool_buckets
+    from .scoring import ScoreBatch, score_and_pool
 
     ctx = ctx or _lib.Context.get()
     forest = model if isinstance(model, DeviceForest) else load_forest(model, ctx)
@@ -78,52 +78,22 @@ def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, mod
     if not live:
         return out
     exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
-    batch = ScoreBatch(4, 400 * res // res, ctx)
+    batch = ScoreBatch(4, 400, ctx)               # upper = 400*res // res (scripts/neoloop-caller:202)
+    chains = []
     for _ID, fu in live:
-        batch.add_assembly(fu._device_assembly())
-    batch.score(forest, exp_arr, prob, forest.w)
-    n_cand, n_scored, n_don = batch.counts()
+        asm = fu._device_assembly()
+        batch.add_assembly(asm)
+        chain_of = np.array([fu.chains[k] for k in range(fu.fusion_matrix.shape[0])])
+        chains.append(chain_of[asm.kept_index()])     # chains[index_map[i]] per gap-free bin
+    loops_by_job, (n_cand, n_scored, n_don) = score_and_pool(batch, forest, exp_arr, prob, res, mmp, chains, nopool)
     if stats is not None:
         stats["candidates"] = stats.get("candidates", 0) + int(n_cand.sum())
         stats["scored"] = stats.get("scored", 0) + int(n_scored.sum())
         stats["donuts"] = stats.get("donuts", 0) + int(n_don.sum())
 
-    # Donuts of every assembly, bucketed by (assembly, chain_i, chain_j) for one pooling launch
-    donuts = []
-    buckets, owners = [], []
     for job, (ID, fu) in enumerate(live):
-        if n_scored[job] < 2:                      # callers.py:619-620
-            donuts.append(None)
-            continue
-        di, dj, dp, dv = batch.donuts(job)
-        donuts.append((di, dj, dp, dv))
-        if nopool or len(di) == 0:
-            continue
-        kept = fu._device_assembly().kept_index()
-        chain_of = np.array([fu.chains[k] for k in range(fu.fusion_matrix.shape[0])])
-        ci, cj = chain_of[kept[di]], chain_of[kept[dj]]
-        key = ci.astype(np.int64) * (1 << 24) + cj
-        for kk in np.unique(key):
-            sel = np.where(key == kk)[0]
-            buckets.append((di[sel], dj[sel], dv[sel]))
-            owners.append((job, sel))
-    masks = pool_buckets(buckets, res, mmp, 15000, ctx) if buckets else []
-    keep_by_job = {}
-    for (job, sel), m in zip(owners, masks):
-        keep_by_job.setdefault(job, []).append(sel[m])
-
-    for job, (ID, fu) in enumerate(live):
-        d = donuts[job]
-        if d is None:
-            loop_index = []
-        else:
-            di, dj, dp, dv = d
-            if nopool:
-                sel = np.arange(len(di))
-            else:
-                parts = keep_by_job.get(job, [])
-                sel = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
-            loop_index = [(int(di[k]), int(dj[k]), float(dp[k])) for k in sel]
+        li, lj, lp = loops_by_job[job]
+        loop_index = [(int(a), int(b), float(p)) for a, b, p in zip(li, lj, lp)]
         loops = fu.index_to_coordinates(loop_index)
         # keep calls inside the ORIGINAL (flexible) assembly only; geometry without re-fetching
         fu2 = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu', expected_values=expected)

@@ -1410,6 +1410,98 @@ NLF_EXPORT int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const i
     return NLF_OK;
 }
 
+static void free_score_outputs(nlf_batch *b)
+{
+    cudaStream_t s = b->ctx->stream;
+    for (auto &j : b->jobs) {
+        if (j.d_prob) { cudaFreeAsync(j.d_prob, s); j.d_prob = nullptr; }
+        if (j.d_slot) { cudaFreeAsync(j.d_slot, s); j.d_slot = nullptr; }
+        if (j.d_don_i) {
+            cudaFreeAsync(j.d_don_i, s); cudaFreeAsync(j.d_don_j, s); cudaFreeAsync(j.d_don_p, s); cudaFreeAsync(j.d_don_v, s);
+            j.d_don_i = j.d_don_j = nullptr; j.d_don_p = j.d_don_v = nullptr;
+        }
+    }
+    if (b->d_hdr) { cudaFreeAsync(b->d_hdr, s); b->d_hdr = nullptr; }
+    if (b->d_featT) { cudaFreeAsync(b->d_featT, s); b->d_featT = nullptr; }
+    if (b->d_group_counter) { cudaFreeAsync(b->d_group_counter, s); b->d_group_counter = nullptr; }
+    if (b->d_overflow) { cudaFreeAsync(b->d_overflow, s); b->d_overflow = nullptr; }
+    if (b->d_exp) { cudaFreeAsync(b->d_exp, s); b->d_exp = nullptr; }
+}
+
+// Forget the results of a scored batch but keep the matrices resident in HBM, so that the
+// whole scoring path (K5-K9) can run again on them.
+NLF_EXPORT int nlf_batch_reset(nlf_batch *b)
+{
+    if (!b) return fail(NLF_ERR_ARG, "nlf_batch_reset: NULL batch");
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    free_score_outputs(b);
+    for (auto &j : b->jobs) {
+        NLF_CUDA(cudaMemsetAsync(j.d_counts, 0, sizeof(unsigned long long) * 4, c->stream));
+        int keep = (j.status == NLF_ERR_LOWER_TRI) ? NLF_ERR_LOWER_TRI : 0;
+        NLF_CUDA(cudaMemcpyAsync(j.d_status, &keep, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        memset(j.counts, 0, sizeof(j.counts));
+    }
+    b->prepared = b->scored = b->counted = false;
+    return NLF_OK;
+}
+
+// Evict the L2 (126 MB on B200) by overwriting a 256 MB scratch buffer on the compute stream.
+NLF_EXPORT int nlf_l2_flush(nlf_ctx *c)
+{
+    NLF_CUDA(cudaSetDevice(c->device));
+    static thread_local void *scratch[16] = {nullptr};
+    const size_t bytes = (size_t)256 << 20;
+    if (c->device >= 16) return fail(NLF_ERR_ARG, "device index too large");
+    if (!scratch[c->device]) NLF_CUDA(cudaMalloc(&scratch[c->device], bytes));
+    NLF_CUDA(cudaMemsetAsync(scratch[c->device], 0, bytes, c->stream));
+    return NLF_OK;
+}
+
+// fp64 add/mul issue-rate micro-benchmark (no FMA): the roofline denominator of the feature
+// kernel, measured in the same run.  16 independent chains per thread, DADD and DMUL alternate.
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+    const double m = 1.0000000001, s = 1e-12;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) { a[k] = __dmul_rn(a[k], m); a[k] = __dadd_rn(a[k], s); }
+    }
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) t += a[k];
+    if (t == 12345.678) out[0] = t;
+}
+
+NLF_EXPORT int nlf_fp64_peak(nlf_ctx *c, double *gops)
+{
+    NLF_CUDA(cudaSetDevice(c->device));
+    double *d;
+    NLF_CUDA(cudaMalloc(&d, 8));
+    const int iters = 4096, threads = 256, blocks = c->sm_count * 8;
+    cudaEvent_t a, b;
+    NLF_CUDA(cudaEventCreate(&a));
+    NLF_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        NLF_CUDA(cudaEventRecord(a, c->stream));
+        k_fp64_peak<<<blocks, threads, 0, c->stream>>>(d, iters);
+        NLF_CUDA(cudaEventRecord(b, c->stream));
+        NLF_CUDA(cudaEventSynchronize(b));
+        float ms;
+        NLF_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    c->launches += 4;
+    double ops = (double)blocks * threads * (double)iters * 32.0;
+    *gops = ops / (best * 1e-3) / 1e9;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return NLF_OK;
+}
+
 NLF_EXPORT int nlf_batch_destroy(nlf_batch *b)
 {
     if (!b) return NLF_OK;

@@ -13,7 +13,8 @@ import numpy as np
 from . import _lib
 from ._lib import check, f64, i32, ptr
 
-__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "pool_buckets", "local_clustering_gpu"]
+__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "pool_buckets", "local_clustering_gpu",
+           "score_and_pool", "score_matrices"]
 
 
 def gaussian_weights(sigma: float = 1.0, truncate: float = 4.0):
@@ -146,6 +147,11 @@ class ScoreBatch:
                                           ptr(gw, C.c_double), radius, float(thre)))
         self._counts = None
         self._keepalive.clear()
+
+    def reset(self):
+        """Forget the results, keep the matrices in HBM (lets the scoring path run again)."""
+        check(_lib.load().nlf_batch_reset(self.h))
+        self._counts = None
 
     # ---- outputs
     def counts(self):
@@ -285,3 +291,68 @@ def local_clustering_gpu(ij, val, res, min_count=2, r=15000, chain_i=None, chain
         for a, b in ij[s][m]:
             out.add((int(a), int(b)))
     return out
+
+
+def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, min_count: int = 2,
+                   chains: Optional[Sequence] = None, no_pool: bool = False, r: int = 15000):
+    """The scoring path for a whole batch: candidates -> features -> forest -> threshold ->
+    pooling (callers.py:614-639 for every matrix of the batch).
+
+    chains[job] = per-gap-free-bin block id (``chains[index_map[i]]`` of the reference) or None.
+    Returns (loops, counts): loops[job] = (i, j, prob) arrays of the called loops, counts =
+    (n_candidates, n_scored, n_donuts) arrays.
+    """
+    batch.score(forest, exp_arr, thre, forest.w)
+    n_cand, n_scored, n_don = batch.counts()
+    donuts = []
+    buckets, owners = [], []
+    for job in range(batch.njobs):
+        if n_scored[job] < 2:                      # callers.py:619-620
+            donuts.append(None)
+            continue
+        di, dj, dp, dv = batch.donuts(job)
+        donuts.append((di, dj, dp, dv))
+        if no_pool or len(di) == 0:
+            continue
+        ch = None if chains is None else chains[job]
+        if ch is None:
+            key = np.zeros(len(di), dtype=np.int64)
+        else:
+            ch = np.asarray(ch)
+            key = ch[di].astype(np.int64) * (1 << 24) + ch[dj]
+        for kk in np.unique(key):
+            sel = np.where(key == kk)[0]
+            buckets.append((di[sel], dj[sel], dv[sel]))
+            owners.append((job, sel))
+    masks = pool_buckets(buckets, res, min_count, r, batch.ctx) if buckets else []
+    keep = {}
+    for (job, sel), m in zip(owners, masks):
+        keep.setdefault(job, []).append(sel[m])
+    loops = []
+    empty = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64))
+    for job in range(batch.njobs):
+        d = donuts[job]
+        if d is None:
+            loops.append(empty)
+            continue
+        di, dj, dp, dv = d
+        if no_pool:
+            sel = np.arange(len(di))
+        else:
+            parts = keep.get(job, [])
+            sel = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+        loops.append((di[sel], dj[sel], dp[sel]))
+    return loops, (n_cand, n_scored, n_don)
+
+
+def score_matrices(mats: Sequence[np.ndarray], forest, exp_arr, thre: float, res: int, min_count: int = 2,
+                   chains: Optional[Sequence] = None, no_pool: bool = False, upper: int = 400, ctx=None):
+    """Host gap-free matrices in -> called loops out, one batch on one GPU (the end-to-end call
+    ``bench.py`` times: host->device copies, every kernel, device->host results)."""
+    batch = ScoreBatch(4, upper, ctx)
+    try:
+        for G in mats:
+            batch.add_dense(G)
+        return score_and_pool(batch, forest, exp_arr, thre, res, min_count, chains, no_pool)
+    finally:
+        batch.close()
