@@ -10,6 +10,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -459,6 +460,97 @@ k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict
     }
 }
 
+// K8 (shared-memory version).  The forest is cut into parts of consecutive trees that fit in
+// shared memory next to the per-warp feature tiles; one launch per part, the running fp64 sum
+// is carried through HBM between parts (8 B per pixel), so the accumulation order stays the
+// estimator order.  Node = 8 bytes, leaves carry their value in place:
+//   internal: .y bit31 = 1, bits 30-23 feature, bit 22 missing_go_to_left, bits 21-0 right child
+//             (index inside the part); .x = float threshold (largest float <= sklearn's float64 one)
+//   leaf    : the 8 bytes are the class-1 fraction as a double (non-negative => bit 63 clear)
+// The left child of node k is k+1.  Every lane walks ILP trees at once with branch-free steps
+// (a finished chain re-reads its leaf), so ILP independent shared-memory loads are in flight
+// per lane; leaf values are then added in tree order.
+constexpr int FOREST_WARPS = 4;
+constexpr int FOREST_ILP = 8;
+
+template <int WARPS, int ILP>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+k_forest_smem(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
+              const GroupHdr *__restrict__ hdr, const float *__restrict__ featT,
+              const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
+              double *__restrict__ accbuf, int first, int last)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int part_base = tree_off[t0];
+    const int part_nodes = tree_off[t1] - part_base;
+    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw);
+    int *soff = reinterpret_cast<int *>(smem_raw + sizeof(uint2) * (size_t)((part_nodes + 2) & ~1));   // 16-byte aligned
+    const int ntree = t1 - t0;
+    const int noff = (ntree + ILP + 3) & ~3;
+    float *fs = reinterpret_cast<float *>(soff + noff);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < part_nodes; k += blockDim.x) snodes[k] = nodes2[part_base + k];
+    if (threadIdx.x == 0) snodes[part_nodes] = make_uint2(0u, 0u);        // padding "tree": a leaf worth +0.0
+    for (int k = threadIdx.x; k < ntree + ILP; k += blockDim.x)
+        soff[k] = (k < ntree) ? tree_off[t0 + k] - part_base : part_nodes;
+    __syncthreads();
+    const char *my = reinterpret_cast<const char *>(fs + (size_t)warp * F * 32 + lane);
+    float *mytile = fs + (size_t)warp * F * 32;
+    const unsigned ngroups = *group_counter;
+    const int dlo = max(lower, W + 2);
+    for (unsigned g = blockIdx.x * WARPS + warp; g < ngroups; g += gridDim.x * WARPS) {
+        const float4 *src = reinterpret_cast<const float4 *>(featT + (size_t)g * F * 32);
+        float4 *dst = reinterpret_cast<float4 *>(mytile);
+        for (int k = lane; k < F * 8; k += 32) dst[k] = __ldcs(&src[k]);
+        __syncwarp();
+        const GroupHdr h = hdr[g];
+        if ((h.mask >> lane) & 1u) {
+            double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
+            for (int t = 0; t < ntree; t += ILP) {
+                int node[ILP];
+                uint2 nd[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; k++) {
+                    node[k] = soff[t + k];
+                    nd[k] = snodes[node[k]];
+                }
+                bool any = true;
+                while (any) {
+                    any = false;
+#pragma unroll
+                    for (int k = 0; k < ILP; k++) {
+                        const unsigned m = nd[k].y;
+                        const bool internal = (int)m < 0;
+                        // byte offset of feature row f in the tile: f * 128 (0 for a finished chain)
+                        const unsigned foff = internal ? ((m >> 16) & 0x7f80u) : 0u;
+                        const float xv = *reinterpret_cast<const float *>(my + foff);
+                        const float thr = __uint_as_float(nd[k].x);
+                        const bool le = xv <= thr;            // false for NaN
+                        const bool leu = !(xv > thr);         // true for NaN
+                        const bool left = (m & 0x400000u) ? leu : le;
+                        int nxt = left ? node[k] + 1 : (int)(m & 0x3fffffu);
+                        nxt = internal ? nxt : node[k];
+                        node[k] = nxt;
+                        any |= internal;
+                    }
+#pragma unroll
+                    for (int k = 0; k < ILP; k++) nd[k] = snodes[node[k]];
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; k++)
+                    acc = __dadd_rn(acc, __hiloint2double((int)nd[k].y, (int)nd[k].x));   // padding adds +0.0
+            }
+            if (last) {
+                const JobDev J = jobs[h.job];
+                J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
+            } else {
+                accbuf[(size_t)g * 32 + lane] = acc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // forest on plain row-major float32 rows (nlf_forest_predict): thread per row
 __global__ void k_forest_rows(ForestDev fr, const float *__restrict__ X, long long N, double *__restrict__ out)
 {
@@ -710,9 +802,12 @@ struct nlf_forest {
     nlf_ctx *ctx;
     ForestDev dev;
     uint2 *d_nodes = nullptr;
+    uint2 *d_nodes2 = nullptr;       // shared-memory format (leaf values in place), NULL if unusable
     double *d_leaf = nullptr;
     int *d_off = nullptr;
     long long n_nodes = 0;
+    std::vector<int> off;            // host copy of tree offsets
+    std::vector<int> part_begin;     // shared-memory parts: trees [part_begin[p], part_begin[p+1])
 };
 
 struct HostJob {
@@ -882,10 +977,65 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
             nodes[(size_t)(b + k)] = nd;
         }
     }
+    // shared-memory format: leaves carry their value in place (needs a clear sign bit); trees are
+    // grouped into parts that fit in shared memory next to FOREST_WARPS feature tiles, and right
+    // children are stored as indices inside their part.
+    std::vector<uint2> nodes2((size_t)total);
+    std::vector<int> part_begin;
+    bool v2_ok = true;
+    {
+        const size_t smem_max = 232448;                   // 227 KB opt-in limit per block on sm_100
+        const size_t feat_bytes = sizeof(float) * (size_t)FOREST_WARPS * n_features * 32;
+        if (feat_bytes + 4096 >= smem_max) v2_ok = false;
+        int t = 0;
+        while (t < n_trees && v2_ok) {
+            part_begin.push_back(t);
+            int t1 = t;
+            while (t1 < n_trees) {
+                size_t nn = (size_t)(tree_off[t1 + 1] - tree_off[t]);
+                size_t need = ((nn + 2) & ~(size_t)1) * 8 + sizeof(int) * (size_t)(((t1 + 1 - t) + FOREST_ILP + 3) & ~3) + feat_bytes;
+                if (need > smem_max) break;
+                t1++;
+            }
+            if (t1 == t) v2_ok = false;                   // a single tree does not fit
+            t = t1;
+        }
+        part_begin.push_back(n_trees);
+    }
+    for (size_t p = 0; v2_ok && p + 1 < part_begin.size(); p++) {
+        const long long pbase = tree_off[part_begin[p]];
+        if (tree_off[part_begin[p + 1]] - pbase >= (1 << 22)) v2_ok = false;
+        for (int t = part_begin[p]; t < part_begin[p + 1] && v2_ok; t++) {
+            long long b = tree_off[t], cnt = tree_off[t + 1] - b;
+            for (long long k = 0; k < cnt; k++) {
+                uint2 nd;
+                if (left[b + k] < 0) {
+                    double v = leaf_p1[b + k];
+                    if (std::signbit(v)) { v2_ok = false; break; }
+                    uint64_t bits;
+                    memcpy(&bits, &v, 8);
+                    nd.x = (unsigned)(bits & 0xffffffffu);
+                    nd.y = (unsigned)(bits >> 32);
+                } else {
+                    nd.x = nodes[(size_t)(b + k)].x;
+                    nd.y = 0x80000000u | ((unsigned)feature[b + k] << 23) |
+                           ((missing_left && missing_left[b + k]) ? 0x400000u : 0u) |
+                           (unsigned)(b - pbase + right[b + k]);
+                }
+                nodes2[(size_t)(b + k)] = nd;
+            }
+        }
+    }
     NLF_CUDA(cudaSetDevice(ctx->device));
     nlf_forest *f = new nlf_forest();
     f->ctx = ctx;
     f->n_nodes = total;
+    f->off = off;
+    f->part_begin = part_begin;
+    if (v2_ok) {
+        NLF_CUDA(cudaMalloc(&f->d_nodes2, sizeof(uint2) * (size_t)total));
+        NLF_CUDA(cudaMemcpy(f->d_nodes2, nodes2.data(), sizeof(uint2) * (size_t)total, cudaMemcpyHostToDevice));
+    }
     NLF_CUDA(cudaMalloc(&f->d_nodes, sizeof(uint2) * (size_t)total));
     NLF_CUDA(cudaMalloc(&f->d_leaf, sizeof(double) * (size_t)total));
     NLF_CUDA(cudaMalloc(&f->d_off, sizeof(int) * (size_t)(n_trees + 1)));
@@ -906,6 +1056,7 @@ NLF_EXPORT int nlf_forest_destroy(nlf_forest *f)
     if (!f) return NLF_OK;
     cudaSetDevice(f->ctx->device);
     cudaFree(f->d_nodes);
+    if (f->d_nodes2) cudaFree(f->d_nodes2);
     cudaFree(f->d_leaf);
     cudaFree(f->d_off);
     delete f;
@@ -1045,6 +1196,42 @@ static int launch_features(nlf_batch *b, int total_tiles, int nexp)
     return NLF_OK;
 }
 
+// K8 launch: shared-memory forest parts when they fit, else the global-memory kernel.
+static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
+{
+    nlf_ctx *c = b->ctx;
+    constexpr int WARPS = FOREST_WARPS, ILP = FOREST_ILP;
+    const size_t smem_max = 232448;
+    const size_t feat_bytes = sizeof(float) * (size_t)WARPS * F * 32;
+    const int T = f->dev.n_trees;
+    if (f->d_nodes2 == nullptr) {
+        constexpr int GW = 4;
+        size_t smem = sizeof(float) * (size_t)GW * F * 32;
+        NLF_CUDA(cudaFuncSetAttribute(k_forest<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KLaunch k(c, P_FOREST);
+        k_forest<GW><<<c->sm_count * 2, 32 * GW, smem, c->stream>>>(f->dev, b->d_hdr, b->d_featT, b->d_group_counter,
+                                                                    b->d_jobs, b->lower, w, b->ndp);
+        NLF_CUDA(cudaGetLastError());
+        return NLF_OK;
+    }
+    const int nparts = (int)f->part_begin.size() - 1;
+    double *acc = nullptr;
+    if (nparts > 1) NLF_CUDA(cudaMallocAsync(&acc, sizeof(double) * (size_t)b->max_groups * 32, c->stream));
+    NLF_CUDA(cudaFuncSetAttribute(k_forest_smem<WARPS, ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    for (int p = 0; p < nparts; p++) {
+        int t0 = f->part_begin[p], t1 = f->part_begin[p + 1];
+        size_t nodes = (size_t)(f->off[t1] - f->off[t0]);
+        size_t smem = ((nodes + 2) & ~(size_t)1) * 8 + sizeof(int) * (size_t)(((t1 - t0) + ILP + 3) & ~3) + feat_bytes;
+        KLaunch k(c, P_FOREST);
+        k_forest_smem<WARPS, ILP><<<c->sm_count, 32 * WARPS, smem, c->stream>>>(
+            f->d_nodes2, f->d_off, t0, t1, T, F, b->d_hdr, b->d_featT, b->d_group_counter, b->d_jobs, b->lower, w,
+            b->ndp, acc, p == 0, p == nparts - 1);
+        NLF_CUDA(cudaGetLastError());
+    }
+    if (acc) NLF_CUDA(cudaFreeAsync(acc, c->stream));
+    return NLF_OK;
+}
+
 // upload the per-job descriptors (pointers that are still NULL stay NULL)
 static int upload_jobs(nlf_batch *b, int w)
 {
@@ -1167,16 +1354,8 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     else if (w == 6) launch_features<6>(b, tiles, nexp);
     else launch_features<7>(b, tiles, nexp);
     NLF_CUDA(cudaGetLastError());
-    {
-        constexpr int WARPS = 4;
-        size_t smem = sizeof(float) * (size_t)WARPS * F * 32;
-        NLF_CUDA(cudaFuncSetAttribute(k_forest<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int grid = c->sm_count * 2;
-        KLaunch k(c, P_FOREST);
-        k_forest<WARPS><<<grid, 32 * WARPS, smem, c->stream>>>(f->dev, b->d_hdr, b->d_featT, b->d_group_counter,
-                                                               b->d_jobs, b->lower, w, b->ndp);
-    }
-    NLF_CUDA(cudaGetLastError());
+    rc = launch_forest(b, f, w, F);
+    if (rc) return rc;
     {
         KLaunch k(c, P_THRESH);
         dim3 grid(64, nj);
