@@ -8,6 +8,7 @@
 // intrinsics (no FMA contraction; the file is also compiled with -fmad=false), in the exact
 // operation order of numpy / scipy.ndimage / sklearn as restated in oracle/c/nlf_oracle.c.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cmath>
@@ -472,6 +473,18 @@ k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict
 // per lane; leaf values are then added in tree order.
 constexpr int FOREST_WARPS = 4;
 constexpr int FOREST_ILP = 8;
+constexpr int COOP_NW = 8;
+constexpr int COOP_ILP = 2;
+
+// dynamic shared memory of k_forest_coop for a part of `nodes` nodes in `ntree` trees
+static inline size_t forest_coop_smem(size_t nodes, int ntree, int F)
+{
+    size_t tiles = 2 * (size_t)F * 128;
+    size_t leafv = 2 * (size_t)ntree * 32 * 8;
+    size_t nd = ((nodes + 2) & ~(size_t)1) * 8;
+    size_t off = sizeof(int) * (size_t)((ntree + 64 + 3) & ~3);
+    return tiles + leafv + nd + off + 128;
+}
 
 template <int WARPS, int ILP>
 __global__ void __launch_bounds__(32 * WARPS, 1)
@@ -548,6 +561,176 @@ k_forest_smem(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
             }
         }
         __syncwarp();
+    }
+}
+
+// K8 (cooperative version).  All warps of a CTA share ONE feature tile (32 pixels x F floats,
+// brought in by a TMA bulk copy, double buffered) and split the part's trees between them; each
+// lane walks its warp's trees back to back without waiting for the other lanes and drops every
+// leaf value into leafv[tree][lane] in shared memory; after a block barrier one warp adds the
+// part's values in tree order (fp64, sequential: sklearn's accumulation order) while the others
+// already traverse the next tile.  Decoupling traversal order from summation order is what
+// allows full lane efficiency AND many resident warps (latency hiding) at the same time.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    const unsigned addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// explicit shared-space accessors (32-bit shared addresses: keeps every access an LDS/STS)
+__device__ __forceinline__ uint2 lds_u2(unsigned a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_i(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_d(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u2(unsigned a, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+
+template <int NW, int ILP>
+__global__ void __launch_bounds__(32 * NW, 1)
+k_forest_coop(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
+              const GroupHdr *__restrict__ hdr, const float *__restrict__ featT,
+              const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
+              double *__restrict__ accbuf, int first, int last)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    constexpr int S = NW * ILP;                                   // tree streams per pixel column
+    const int part_base = tree_off[t0];
+    const int part_nodes = tree_off[t1] - part_base;
+    const int ntree = t1 - t0;
+    const unsigned tile_bytes = (unsigned)F * 128u;
+    const unsigned leafv_bytes = (unsigned)ntree * 256u;
+    // layout: [tile0][tile1][leafv0][leafv1][nodes][soff]
+    const unsigned a_base = smem_u32(smem_raw);
+    const unsigned a_tile = a_base;
+    const unsigned a_leafv = a_base + 2 * tile_bytes;
+    const unsigned a_nodes = a_leafv + 2 * leafv_bytes;
+    const unsigned a_soff = a_nodes + (unsigned)((part_nodes + 2) & ~1) * 8u;
+    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + 2 * (size_t)tile_bytes + 2 * (size_t)leafv_bytes);
+    int *soff = reinterpret_cast<int *>(snodes + ((part_nodes + 2) & ~1));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < part_nodes; k += blockDim.x) snodes[k] = nodes2[part_base + k];
+    if (tid == 0) snodes[part_nodes] = make_uint2(0u, 0u);        // dummy leaf for exhausted streams
+    for (int k = tid; k < ntree + S; k += blockDim.x)
+        soff[k] = (k < ntree) ? tree_off[t0 + k] - part_base : part_nodes;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned ngroups = *group_counter;
+    const int dlo = max(lower, W + 2);
+    unsigned g = blockIdx.x;
+    if (g < ngroups && tid == 0) {
+        mbar_expect_tx(&mbar[0], tile_bytes);
+        tma_load_1d(smem_raw, featT + (size_t)g * F * 32, tile_bytes, &mbar[0]);
+    }
+    GroupHdr h = (g < ngroups) ? hdr[g] : GroupHdr{0, 0, 0, 0u};
+    for (unsigned it = 0; g < ngroups; it++, g += gridDim.x) {
+        const unsigned buf = it & 1u;
+        const unsigned gn = g + gridDim.x;
+        if (gn < ngroups && tid == 0) {
+            // tile[buf^1] was last read during iteration it-1, which ended with a block barrier
+            mbar_expect_tx(&mbar[buf ^ 1u], tile_bytes);
+            tma_load_1d(smem_raw + (size_t)(buf ^ 1u) * tile_bytes, featT + (size_t)gn * F * 32, tile_bytes, &mbar[buf ^ 1u]);
+        }
+        GroupHdr hn = (gn < ngroups) ? hdr[gn] : GroupHdr{0, 0, 0, 0u};      // prefetch the next header
+        mbar_wait(&mbar[buf], (it >> 1) & 1u);
+        const bool active = (h.mask >> lane) & 1u;
+        if (active) {
+            const unsigned my = a_tile + buf * tile_bytes + (unsigned)lane * 4u;
+            const unsigned lv = a_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+            int ti[ILP], node[ILP];
+            uint2 nd[ILP];
+#pragma unroll
+            for (int k = 0; k < ILP; k++) {
+                ti[k] = warp * ILP + k;                       // stream: trees (warp*ILP+k) + S*i
+                node[k] = lds_i(a_soff + 4u * (unsigned)min(ti[k], ntree));
+            }
+#pragma unroll
+            for (int k = 0; k < ILP; k++) nd[k] = lds_u2(a_nodes + 8u * (unsigned)node[k]);
+            bool busy = true;
+            while (busy) {
+                busy = false;
+#pragma unroll
+                for (int k = 0; k < ILP; k++) {
+                    const unsigned m = nd[k].y;
+                    if ((int)m < 0) {                          // internal node: one comparison
+                        const float xv = lds_f(my + ((m >> 16) & 0x7f80u));
+                        const float thr = __uint_as_float(nd[k].x);
+                        const bool left = (m & 0x400000u) ? !(xv > thr) : (xv <= thr);
+                        node[k] = left ? node[k] + 1 : (int)(m & 0x3fffffu);
+                        busy = true;
+                    } else if (ti[k] < ntree) {                // leaf: publish, move to the stream's next tree
+                        sts_u2(lv + 256u * (unsigned)ti[k], nd[k]);
+                        ti[k] += S;
+                        node[k] = lds_i(a_soff + 4u * (unsigned)min(ti[k], ntree));
+                        busy = true;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; k++) nd[k] = lds_u2(a_nodes + 8u * (unsigned)node[k]);
+            }
+        }
+        __syncthreads();
+        if (warp == (int)(it % NW) && active) {
+            const unsigned lv = a_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+            double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
+            for (int t = 0; t < ntree; t++) acc = __dadd_rn(acc, lds_d(lv + 256u * (unsigned)t));
+            if (last) {
+                const JobDev J = jobs[h.job];
+                J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
+            } else {
+                accbuf[(size_t)g * 32 + lane] = acc;
+            }
+        }
+        h = hn;
     }
 }
 
@@ -984,8 +1167,8 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
     std::vector<int> part_begin;
     bool v2_ok = true;
     {
-        const size_t smem_max = 232448;                   // 227 KB opt-in limit per block on sm_100
-        const size_t feat_bytes = sizeof(float) * (size_t)FOREST_WARPS * n_features * 32;
+        const size_t smem_max = 232448 - 64;              // 227 KB opt-in limit per block on sm_100 (minus static)
+        const size_t feat_bytes = 2 * sizeof(float) * (size_t)n_features * 32;       // two feature tiles
         if (feat_bytes + 4096 >= smem_max) v2_ok = false;
         int t = 0;
         while (t < n_trees && v2_ok) {
@@ -993,7 +1176,7 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
             int t1 = t;
             while (t1 < n_trees) {
                 size_t nn = (size_t)(tree_off[t1 + 1] - tree_off[t]);
-                size_t need = ((nn + 2) & ~(size_t)1) * 8 + sizeof(int) * (size_t)(((t1 + 1 - t) + FOREST_ILP + 3) & ~3) + feat_bytes;
+                size_t need = forest_coop_smem(nn, t1 + 1 - t, n_features);
                 if (need > smem_max) break;
                 t1++;
             }
@@ -1200,9 +1383,7 @@ static int launch_features(nlf_batch *b, int total_tiles, int nexp)
 static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
 {
     nlf_ctx *c = b->ctx;
-    constexpr int WARPS = FOREST_WARPS, ILP = FOREST_ILP;
     const size_t smem_max = 232448;
-    const size_t feat_bytes = sizeof(float) * (size_t)WARPS * F * 32;
     const int T = f->dev.n_trees;
     if (f->d_nodes2 == nullptr) {
         constexpr int GW = 4;
@@ -1217,15 +1398,41 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
     const int nparts = (int)f->part_begin.size() - 1;
     double *acc = nullptr;
     if (nparts > 1) NLF_CUDA(cudaMallocAsync(&acc, sizeof(double) * (size_t)b->max_groups * 32, c->stream));
-    NLF_CUDA(cudaFuncSetAttribute(k_forest_smem<WARPS, ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char *e = getenv("NLF_FOREST_CFG");              // tuning knob: "<warps>x<ilp>"
+        cfg = 1;
+        if (e) {
+            if (!strcmp(e, "8x2")) cfg = 0;
+            else if (!strcmp(e, "16x1")) cfg = 1;
+            else if (!strcmp(e, "16x2")) cfg = 2;
+            else if (!strcmp(e, "12x1")) cfg = 3;
+            else if (!strcmp(e, "10x1")) cfg = 4;
+            else if (!strcmp(e, "8x1")) cfg = 5;
+        }
+    }
     for (int p = 0; p < nparts; p++) {
         int t0 = f->part_begin[p], t1 = f->part_begin[p + 1];
         size_t nodes = (size_t)(f->off[t1] - f->off[t0]);
-        size_t smem = ((nodes + 2) & ~(size_t)1) * 8 + sizeof(int) * (size_t)(((t1 - t0) + ILP + 3) & ~3) + feat_bytes;
+        size_t smem = forest_coop_smem(nodes, t1 - t0, F);
         KLaunch k(c, P_FOREST);
-        k_forest_smem<WARPS, ILP><<<c->sm_count, 32 * WARPS, smem, c->stream>>>(
-            f->d_nodes2, f->d_off, t0, t1, T, F, b->d_hdr, b->d_featT, b->d_group_counter, b->d_jobs, b->lower, w,
-            b->ndp, acc, p == 0, p == nparts - 1);
+#define NLF_LAUNCH_COOP(NWv, ILPv)                                                                                  \
+        do {                                                                                                        \
+            NLF_CUDA(cudaFuncSetAttribute(k_forest_coop<NWv, ILPv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          (int)(smem_max - 64)));                                                   \
+            k_forest_coop<NWv, ILPv><<<c->sm_count, 32 * NWv, smem, c->stream>>>(                                   \
+                f->d_nodes2, f->d_off, t0, t1, T, F, b->d_hdr, b->d_featT, b->d_group_counter, b->d_jobs, b->lower, \
+                w, b->ndp, acc, p == 0, p == nparts - 1);                                                           \
+        } while (0)
+        switch (cfg) {
+            case 0: NLF_LAUNCH_COOP(8, 2); break;
+            case 2: NLF_LAUNCH_COOP(16, 2); break;
+            case 3: NLF_LAUNCH_COOP(12, 1); break;
+            case 4: NLF_LAUNCH_COOP(10, 1); break;
+            case 5: NLF_LAUNCH_COOP(8, 1); break;
+            default: NLF_LAUNCH_COOP(16, 1); break;
+        }
+#undef NLF_LAUNCH_COOP
         NLF_CUDA(cudaGetLastError());
     }
     if (acc) NLF_CUDA(cudaFreeAsync(acc, c->stream));
