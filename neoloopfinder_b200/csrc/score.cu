@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(FeatCfg<W>::NT, 1)
 k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int lower, int upper,
            int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, GroupHdr *__restrict__ hdr,
            float *__restrict__ featT, unsigned *__restrict__ group_counter, unsigned max_groups,
-           int *__restrict__ overflow)
+           int *__restrict__ overflow, unsigned *__restrict__ nanmask)
 {
     using C = FeatCfg<W>;
     constexpr int S = C::S, F = C::F, TX = C::TX, TR = C::TR, TC = C::TC, VC = C::VC, NT = C::NT;
@@ -381,13 +381,21 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
                 mx = (v > mx) ? v : mx;
             }
             if (nn) { mn = qnan; mx = qnan; }
+            bool f_nan = false;
             if ((mm >> lane) & 1u) {
                 double den = __dsub_rn(mx, mn);
 #pragma unroll
                 for (int b = 0; b < S; b++) {
                     double f = __ddiv_rn(__dsub_rn(out[b], mn), den);
+                    f_nan |= (f != f);
                     fdst[(size_t)(warp * S + b) * 32 + lane] = __double2float_rn(f);
                 }
+            }
+            // windows with NaN features (constant window, or a zero in the expected table) take the
+            // general forest kernel, which implements sklearn's missing_go_to_left routing
+            {
+                unsigned nb = __ballot_sync(0xffffffffu, f_nan);
+                if (lane == 0 && nb) atomicOr(&nanmask[g], nb);
             }
             // red_* are rewritten only after the next stage-A barrier; Vx only after this point
             __syncthreads();
@@ -461,116 +469,7 @@ k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict
     }
 }
 
-// K8 (shared-memory version).  The forest is cut into parts of consecutive trees that fit in
-// shared memory next to the per-warp feature tiles; one launch per part, the running fp64 sum
-// is carried through HBM between parts (8 B per pixel), so the accumulation order stays the
-// estimator order.  Node = 8 bytes, leaves carry their value in place:
-//   internal: .y bit31 = 1, bits 30-23 feature, bit 22 missing_go_to_left, bits 21-0 right child
-//             (index inside the part); .x = float threshold (largest float <= sklearn's float64 one)
-//   leaf    : the 8 bytes are the class-1 fraction as a double (non-negative => bit 63 clear)
-// The left child of node k is k+1.  Every lane walks ILP trees at once with branch-free steps
-// (a finished chain re-reads its leaf), so ILP independent shared-memory loads are in flight
-// per lane; leaf values are then added in tree order.
-constexpr int FOREST_WARPS = 4;
-constexpr int FOREST_ILP = 8;
-constexpr int COOP_NW = 8;
-constexpr int COOP_ILP = 2;
-
-// dynamic shared memory of k_forest_coop for a part of `nodes` nodes in `ntree` trees
-static inline size_t forest_coop_smem(size_t nodes, int ntree, int F)
-{
-    size_t tiles = 2 * (size_t)F * 128;
-    size_t leafv = 2 * (size_t)ntree * 32 * 8;
-    size_t nd = ((nodes + 2) & ~(size_t)1) * 8;
-    size_t off = sizeof(int) * (size_t)((ntree + 64 + 3) & ~3);
-    return tiles + leafv + nd + off + 128;
-}
-
-template <int WARPS, int ILP>
-__global__ void __launch_bounds__(32 * WARPS, 1)
-k_forest_smem(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
-              const GroupHdr *__restrict__ hdr, const float *__restrict__ featT,
-              const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
-              double *__restrict__ accbuf, int first, int last)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int part_base = tree_off[t0];
-    const int part_nodes = tree_off[t1] - part_base;
-    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw);
-    int *soff = reinterpret_cast<int *>(smem_raw + sizeof(uint2) * (size_t)((part_nodes + 2) & ~1));   // 16-byte aligned
-    const int ntree = t1 - t0;
-    const int noff = (ntree + ILP + 3) & ~3;
-    float *fs = reinterpret_cast<float *>(soff + noff);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < part_nodes; k += blockDim.x) snodes[k] = nodes2[part_base + k];
-    if (threadIdx.x == 0) snodes[part_nodes] = make_uint2(0u, 0u);        // padding "tree": a leaf worth +0.0
-    for (int k = threadIdx.x; k < ntree + ILP; k += blockDim.x)
-        soff[k] = (k < ntree) ? tree_off[t0 + k] - part_base : part_nodes;
-    __syncthreads();
-    const char *my = reinterpret_cast<const char *>(fs + (size_t)warp * F * 32 + lane);
-    float *mytile = fs + (size_t)warp * F * 32;
-    const unsigned ngroups = *group_counter;
-    const int dlo = max(lower, W + 2);
-    for (unsigned g = blockIdx.x * WARPS + warp; g < ngroups; g += gridDim.x * WARPS) {
-        const float4 *src = reinterpret_cast<const float4 *>(featT + (size_t)g * F * 32);
-        float4 *dst = reinterpret_cast<float4 *>(mytile);
-        for (int k = lane; k < F * 8; k += 32) dst[k] = __ldcs(&src[k]);
-        __syncwarp();
-        const GroupHdr h = hdr[g];
-        if ((h.mask >> lane) & 1u) {
-            double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
-            for (int t = 0; t < ntree; t += ILP) {
-                int node[ILP];
-                uint2 nd[ILP];
-#pragma unroll
-                for (int k = 0; k < ILP; k++) {
-                    node[k] = soff[t + k];
-                    nd[k] = snodes[node[k]];
-                }
-                bool any = true;
-                while (any) {
-                    any = false;
-#pragma unroll
-                    for (int k = 0; k < ILP; k++) {
-                        const unsigned m = nd[k].y;
-                        const bool internal = (int)m < 0;
-                        // byte offset of feature row f in the tile: f * 128 (0 for a finished chain)
-                        const unsigned foff = internal ? ((m >> 16) & 0x7f80u) : 0u;
-                        const float xv = *reinterpret_cast<const float *>(my + foff);
-                        const float thr = __uint_as_float(nd[k].x);
-                        const bool le = xv <= thr;            // false for NaN
-                        const bool leu = !(xv > thr);         // true for NaN
-                        const bool left = (m & 0x400000u) ? leu : le;
-                        int nxt = left ? node[k] + 1 : (int)(m & 0x3fffffu);
-                        nxt = internal ? nxt : node[k];
-                        node[k] = nxt;
-                        any |= internal;
-                    }
-#pragma unroll
-                    for (int k = 0; k < ILP; k++) nd[k] = snodes[node[k]];
-                }
-#pragma unroll
-                for (int k = 0; k < ILP; k++)
-                    acc = __dadd_rn(acc, __hiloint2double((int)nd[k].y, (int)nd[k].x));   // padding adds +0.0
-            }
-            if (last) {
-                const JobDev J = jobs[h.job];
-                J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
-            } else {
-                accbuf[(size_t)g * 32 + lane] = acc;
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// K8 (cooperative version).  All warps of a CTA share ONE feature tile (32 pixels x F floats,
-// brought in by a TMA bulk copy, double buffered) and split the part's trees between them; each
-// lane walks its warp's trees back to back without waiting for the other lanes and drops every
-// leaf value into leafv[tree][lane] in shared memory; after a block barrier one warp adds the
-// part's values in tree order (fp64, sequential: sklearn's accumulation order) while the others
-// already traverse the next tile.  Decoupling traversal order from summation order is what
-// allows full lane efficiency AND many resident warps (latency hiding) at the same time.
+// shared-memory / mbarrier / TMA helpers for the cooperative forest kernels
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
@@ -600,69 +499,75 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// explicit shared-space accessors (32-bit shared addresses: keeps every access an LDS/STS)
-__device__ __forceinline__ uint2 lds_u2(unsigned a)
+// tree (0..ntree-1) that owns part-local node k; off[] = part-local tree offsets, off[ntree] = part_nodes
+__device__ __forceinline__ int tree_of_node(const int *off, int ntree, int k)
 {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float lds_f(unsigned a)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ int lds_i(unsigned a)
-{
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ double lds_d(unsigned a)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_u2(unsigned a, uint2 v)
-{
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+    int lo = 0, hi = ntree;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= k) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
-template <int NW, int ILP>
+// K8 (cooperative, dynamic trees) -- the production forest kernel.
+// One CTA = 16 warps share ONE feature tile (32 pixels x F floats, TMA bulk copy, double buffered)
+// and the part of the forest held in shared memory.  Lane l of every warp works for pixel l:
+// it grabs the pixel's next unstarted tree from a shared-memory counter, walks it to the leaf,
+// publishes the leaf value in leafv[tree][l] and grabs again, so all 16 lanes-per-pixel stay busy
+// until the part's trees are exhausted (no static imbalance, no lock-step between lanes).
+// After a block barrier one warp adds the part's leaf values in tree order (fp64, sequential =
+// sklearn's accumulation order) while the others already traverse the next tile.
+// Pixels whose features contain NaN are skipped here (nanmask) and scored by k_forest_nan.
+template <int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
-k_forest_coop(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
-              const GroupHdr *__restrict__ hdr, const float *__restrict__ featT,
-              const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
-              double *__restrict__ accbuf, int first, int last)
+k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
+             const GroupHdr *__restrict__ hdr, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
+             const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
+             double *__restrict__ accbuf, int first, int last)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar[2];
-    constexpr int S = NW * ILP;                                   // tree streams per pixel column
     const int part_base = tree_off[t0];
     const int part_nodes = tree_off[t1] - part_base;
     const int ntree = t1 - t0;
     const unsigned tile_bytes = (unsigned)F * 128u;
     const unsigned leafv_bytes = (unsigned)ntree * 256u;
-    // layout: [tile0][tile1][leafv0][leafv1][nodes][soff]
-    const unsigned a_base = smem_u32(smem_raw);
-    const unsigned a_tile = a_base;
-    const unsigned a_leafv = a_base + 2 * tile_bytes;
-    const unsigned a_nodes = a_leafv + 2 * leafv_bytes;
-    const unsigned a_soff = a_nodes + (unsigned)((part_nodes + 2) & ~1) * 8u;
-    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + 2 * (size_t)tile_bytes + 2 * (size_t)leafv_bytes);
-    int *soff = reinterpret_cast<int *>(snodes + ((part_nodes + 2) & ~1));
+    // byte offsets in smem_raw: [tile0][tile1][leafv0][leafv1][cnt0 cnt1][nodes + dummy][roots]
+    const unsigned o_leafv = 2 * tile_bytes;
+    const unsigned o_cnt = o_leafv + 2 * leafv_bytes;
+    const unsigned o_nodes = o_cnt + 256u;
+    const unsigned o_root = o_nodes + (unsigned)((part_nodes + 2) & ~1) * 8u;
+#define SM_U2(off) (*reinterpret_cast<uint2 *>(smem_raw + (off)))
+#define SM_U32(off) (*reinterpret_cast<unsigned *>(smem_raw + (off)))
+#define SM_F32(off) (*reinterpret_cast<float *>(smem_raw + (off)))
+#define SM_F64(off) (*reinterpret_cast<double *>(smem_raw + (off)))
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < part_nodes; k += blockDim.x) snodes[k] = nodes2[part_base + k];
-    if (tid == 0) snodes[part_nodes] = make_uint2(0u, 0u);        // dummy leaf for exhausted streams
-    for (int k = tid; k < ntree + S; k += blockDim.x)
-        soff[k] = (k < ntree) ? tree_off[t0 + k] - part_base : part_nodes;
+    for (int k = tid; k <= ntree; k += blockDim.x)
+        SM_U32(o_root + 4u * k) = (unsigned)((k < ntree) ? tree_off[t0 + k] - part_base : part_nodes);
+    if (tid < 64) SM_U32(o_cnt + 4u * tid) = 0u;
+    __syncthreads();
+    for (int k = tid; k < part_nodes; k += blockDim.x) {
+        uint2 nd = nodes2[part_base + k];
+        if ((int)nd.y < 0) {
+            // {flag | feature<<23 | miss<<22 | tree-local right}  ->  {flag | right byte offset | feature*128>>7}
+            unsigned r = (nd.y & 0x3fffffu) +
+                         SM_U32(o_root + 4u * tree_of_node(reinterpret_cast<const int *>(smem_raw + o_root), ntree, k));
+            unsigned feat = (nd.y >> 23) & 0xffu;
+            // bits 0-7 feature, bits 8-30 right-child byte offset / 8 is not needed: store the byte
+            // offset itself in bits 8-30 (< 2^18 for any part that fits in shared memory)
+            nd.y = 0x80000000u | ((o_nodes + (r << 3)) << 8) | feat;
+        }
+        SM_U2(o_nodes + 8u * k) = nd;
+    }
     if (tid == 0) {
+        SM_U2(o_nodes + 8u * part_nodes) = make_uint2(0u, 0u);
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = o_nodes + 8u * SM_U32(o_root + 4u * k);
     __syncthreads();
     const unsigned ngroups = *group_counter;
     const int dlo = max(lower, W + 2);
@@ -672,6 +577,7 @@ k_forest_coop(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
         tma_load_1d(smem_raw, featT + (size_t)g * F * 32, tile_bytes, &mbar[0]);
     }
     GroupHdr h = (g < ngroups) ? hdr[g] : GroupHdr{0, 0, 0, 0u};
+    unsigned nanm = (g < ngroups) ? nanmask[g] : 0u;
     for (unsigned it = 0; g < ngroups; it++, g += gridDim.x) {
         const unsigned buf = it & 1u;
         const unsigned gn = g + gridDim.x;
@@ -680,57 +586,214 @@ k_forest_coop(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
             mbar_expect_tx(&mbar[buf ^ 1u], tile_bytes);
             tma_load_1d(smem_raw + (size_t)(buf ^ 1u) * tile_bytes, featT + (size_t)gn * F * 32, tile_bytes, &mbar[buf ^ 1u]);
         }
-        GroupHdr hn = (gn < ngroups) ? hdr[gn] : GroupHdr{0, 0, 0, 0u};      // prefetch the next header
+        const GroupHdr hn = (gn < ngroups) ? hdr[gn] : GroupHdr{0, 0, 0, 0u};      // prefetch the next header
+        const unsigned nanm_n = (gn < ngroups) ? nanmask[gn] : 0u;
         mbar_wait(&mbar[buf], (it >> 1) & 1u);
-        const bool active = (h.mask >> lane) & 1u;
+        const bool active = ((h.mask & ~nanm) >> lane) & 1u;
         if (active) {
-            const unsigned my = a_tile + buf * tile_bytes + (unsigned)lane * 4u;
-            const unsigned lv = a_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
-            int ti[ILP], node[ILP];
-            uint2 nd[ILP];
-#pragma unroll
-            for (int k = 0; k < ILP; k++) {
-                ti[k] = warp * ILP + k;                       // stream: trees (warp*ILP+k) + S*i
-                node[k] = lds_i(a_soff + 4u * (unsigned)min(ti[k], ntree));
-            }
-#pragma unroll
-            for (int k = 0; k < ILP; k++) nd[k] = lds_u2(a_nodes + 8u * (unsigned)node[k]);
-            bool busy = true;
-            while (busy) {
-                busy = false;
-#pragma unroll
-                for (int k = 0; k < ILP; k++) {
-                    const unsigned m = nd[k].y;
-                    if ((int)m < 0) {                          // internal node: one comparison
-                        const float xv = lds_f(my + ((m >> 16) & 0x7f80u));
-                        const float thr = __uint_as_float(nd[k].x);
-                        const bool left = (m & 0x400000u) ? !(xv > thr) : (xv <= thr);
-                        node[k] = left ? node[k] + 1 : (int)(m & 0x3fffffu);
-                        busy = true;
-                    } else if (ti[k] < ntree) {                // leaf: publish, move to the stream's next tree
-                        sts_u2(lv + 256u * (unsigned)ti[k], nd[k]);
-                        ti[k] += S;
-                        node[k] = lds_i(a_soff + 4u * (unsigned)min(ti[k], ntree));
-                        busy = true;
-                    }
+            const unsigned my = buf * tile_bytes + (unsigned)lane * 4u;
+            const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+            unsigned *cnt = reinterpret_cast<unsigned *>(smem_raw + o_cnt + buf * 128u + (unsigned)lane * 4u);
+            int t = (int)atomicAdd(cnt, 1u);
+            while (t < ntree) {
+                unsigned na = SM_U32(o_root + 4u * (unsigned)t);
+                uint2 nd = SM_U2(na);
+                while ((int)nd.y < 0) {
+                    const float xv = SM_F32(my + ((nd.y & 0xffu) << 7));
+                    na = (xv <= __uint_as_float(nd.x)) ? na + 8u : ((nd.y >> 8) & 0x7fffffu);
+                    nd = SM_U2(na);
                 }
-#pragma unroll
-                for (int k = 0; k < ILP; k++) nd[k] = lds_u2(a_nodes + 8u * (unsigned)node[k]);
+                SM_U2(lv + 256u * (unsigned)t) = nd;
+                t = (int)atomicAdd(cnt, 1u);
             }
         }
         __syncthreads();
-        if (warp == (int)(it % NW) && active) {
-            const unsigned lv = a_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
-            double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
-            for (int t = 0; t < ntree; t++) acc = __dadd_rn(acc, lds_d(lv + 256u * (unsigned)t));
-            if (last) {
-                const JobDev J = jobs[h.job];
-                J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
-            } else {
-                accbuf[(size_t)g * 32 + lane] = acc;
+        if (warp == (int)(it % NW)) {
+            SM_U32(o_cnt + buf * 128u + (unsigned)lane * 4u) = 0u;       // next use is two barriers away
+            if (active) {
+                const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+                double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
+                for (int tt = 0; tt < ntree; tt++) acc = __dadd_rn(acc, SM_F64(lv + 256u * (unsigned)tt));
+                if (last) {
+                    const JobDev J = jobs[h.job];
+                    J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
+                } else {
+                    accbuf[(size_t)g * 32 + lane] = acc;
+                }
             }
         }
         h = hn;
+        nanm = nanm_n;
+    }
+#undef SM_U2
+#undef SM_U32
+#undef SM_F32
+#undef SM_F64
+}
+
+// K8 (cooperative, dynamic trees, barrier-free pipeline).  Same work decomposition as
+// k_forest_dyn, but consecutive tiles overlap: there is no block barrier.  Every tile buffer has
+// a `full` mbarrier (completed by the TMA copy) and a `done` mbarrier (every thread arrives once
+// it finds no unstarted tree left for that tile).  Threads that run out of trees move on to the
+// next tile at once; the tile's summing warp (round robin) waits for `done`, adds the leaf values
+// in tree order, resets the tree counters and only then issues the TMA copy that refills the
+// buffer two tiles later -- which is also what protects leafv/cnt from early reuse.
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 1)
+k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
+              const GroupHdr *__restrict__ hdr, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
+              const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
+              double *__restrict__ accbuf, int first, int last)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[2], done[2];
+    const int part_base = tree_off[t0];
+    const int part_nodes = tree_off[t1] - part_base;
+    const int ntree = t1 - t0;
+    const unsigned tile_bytes = (unsigned)F * 128u;
+    const unsigned leafv_bytes = (unsigned)ntree * 256u;
+    const unsigned o_leafv = 2 * tile_bytes;
+    const unsigned o_cnt = o_leafv + 2 * leafv_bytes;
+    const unsigned o_nodes = o_cnt + 256u;
+    const unsigned o_root = o_nodes + (unsigned)((part_nodes + 2) & ~1) * 8u;
+#define SM_U2(off) (*reinterpret_cast<uint2 *>(smem_raw + (off)))
+#define SM_U32(off) (*reinterpret_cast<unsigned *>(smem_raw + (off)))
+#define SM_F32(off) (*reinterpret_cast<float *>(smem_raw + (off)))
+#define SM_F64(off) (*reinterpret_cast<double *>(smem_raw + (off)))
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k <= ntree; k += blockDim.x)
+        SM_U32(o_root + 4u * k) = (unsigned)((k < ntree) ? tree_off[t0 + k] - part_base : part_nodes);
+    if (tid < 64) SM_U32(o_cnt + 4u * tid) = 0u;
+    __syncthreads();
+    for (int k = tid; k < part_nodes; k += blockDim.x) {
+        uint2 nd = nodes2[part_base + k];
+        if ((int)nd.y < 0) {
+            unsigned r = (nd.y & 0x3fffffu) +
+                         SM_U32(o_root + 4u * tree_of_node(reinterpret_cast<const int *>(smem_raw + o_root), ntree, k));
+            unsigned feat = (nd.y >> 23) & 0xffu;
+            nd.y = 0x80000000u | ((o_nodes + (r << 3)) << 8) | feat;
+        }
+        SM_U2(o_nodes + 8u * k) = nd;
+    }
+    if (tid == 0) {
+        SM_U2(o_nodes + 8u * part_nodes) = make_uint2(0u, 0u);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&done[0], 32 * NW);
+        mbar_init(&done[1], 32 * NW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = o_nodes + 8u * SM_U32(o_root + 4u * k);
+    __syncthreads();
+    const unsigned ngroups = *group_counter;
+    const int dlo = max(lower, W + 2);
+    const unsigned stride = gridDim.x;
+    unsigned g = blockIdx.x;
+    if (tid == 0) {
+        if (g < ngroups) {
+            mbar_expect_tx(&full[0], tile_bytes);
+            tma_load_1d(smem_raw, featT + (size_t)g * F * 32, tile_bytes, &full[0]);
+        }
+        if (g + stride < ngroups) {
+            mbar_expect_tx(&full[1], tile_bytes);
+            tma_load_1d(smem_raw + tile_bytes, featT + (size_t)(g + stride) * F * 32, tile_bytes, &full[1]);
+        }
+    }
+    GroupHdr h = (g < ngroups) ? hdr[g] : GroupHdr{0, 0, 0, 0u};
+    unsigned nanm = (g < ngroups) ? nanmask[g] : 0u;
+    for (unsigned it = 0; g < ngroups; it++, g += stride) {
+        const unsigned buf = it & 1u;
+        const unsigned par = (it >> 1) & 1u;
+        const unsigned gn = g + stride;
+        const GroupHdr hn = (gn < ngroups) ? hdr[gn] : GroupHdr{0, 0, 0, 0u};
+        const unsigned nanm_n = (gn < ngroups) ? nanmask[gn] : 0u;
+        mbar_wait(&full[buf], par);
+        const bool active = ((h.mask & ~nanm) >> lane) & 1u;
+        if (active) {
+            const unsigned my = buf * tile_bytes + (unsigned)lane * 4u;
+            const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+            unsigned *cnt = reinterpret_cast<unsigned *>(smem_raw + o_cnt + buf * 128u + (unsigned)lane * 4u);
+            int t = (int)atomicAdd(cnt, 1u);
+            while (t < ntree) {
+                unsigned na = SM_U32(o_root + 4u * (unsigned)t);
+                uint2 nd = SM_U2(na);
+                while ((int)nd.y < 0) {
+                    const float xv = SM_F32(my + ((nd.y & 0xffu) << 7));
+                    na = (xv <= __uint_as_float(nd.x)) ? na + 8u : ((nd.y >> 8) & 0x7fffffu);
+                    nd = SM_U2(na);
+                }
+                SM_U2(lv + 256u * (unsigned)t) = nd;
+                t = (int)atomicAdd(cnt, 1u);
+            }
+        }
+        mbar_arrive(&done[buf]);                      // release: this thread's leaf values are published
+        if (warp == (int)(it % NW)) {
+            mbar_wait(&done[buf], par);               // acquire: every thread is through with this tile
+            if (active) {
+                const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+                double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
+                for (int tt = 0; tt < ntree; tt++) acc = __dadd_rn(acc, SM_F64(lv + 256u * (unsigned)tt));
+                if (last) {
+                    const JobDev J = jobs[h.job];
+                    J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
+                } else {
+                    accbuf[(size_t)g * 32 + lane] = acc;
+                }
+            }
+            SM_U32(o_cnt + buf * 128u + (unsigned)lane * 4u) = 0u;
+            __syncwarp();
+            const unsigned g2 = g + 2 * stride;
+            if (lane == 0 && g2 < ngroups) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads/writes before the async-proxy write
+                mbar_expect_tx(&full[buf], tile_bytes);
+                tma_load_1d(smem_raw + (size_t)buf * tile_bytes, featT + (size_t)g2 * F * 32, tile_bytes, &full[buf]);
+            }
+        }
+        h = hn;
+        nanm = nanm_n;
+    }
+#undef SM_U2
+#undef SM_U32
+#undef SM_F32
+#undef SM_F64
+}
+
+// pixels with NaN features: general traversal from global memory with missing_go_to_left routing
+__global__ void k_forest_nan(ForestDev fr, const GroupHdr *__restrict__ hdr, const unsigned *__restrict__ nanmask,
+                             const float *__restrict__ featT, const unsigned *__restrict__ group_counter,
+                             const JobDev *__restrict__ jobs, int lower, int W, int ndp)
+{
+    const unsigned ngroups = *group_counter;
+    const int lane = threadIdx.x & 31;
+    const int dlo = max(lower, W + 2);
+    const int F = fr.n_features;
+    for (unsigned g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * (blockDim.x >> 5)) {
+        const unsigned nm = nanmask[g];
+        if (!nm) continue;
+        const GroupHdr h = hdr[g];
+        if (!(((h.mask & nm) >> lane) & 1u)) continue;
+        const float *x = featT + (size_t)g * F * 32 + lane;
+        double acc = 0.0;
+        for (int t = 0; t < fr.n_trees; t++) {
+            int base = fr.tree_off[t], node = 0;
+            while (true) {
+                uint2 nd = fr.nodes[base + node];
+                unsigned f = nd.y & 0xffu;
+                if (f == 0xffu) break;
+                float xv = x[(size_t)f * 32];
+                bool left = (xv != xv) ? ((nd.y >> 8) & 1u) : (xv <= __uint_as_float(nd.x));
+                node = left ? node + 1 : (int)(nd.y >> 9);
+            }
+            acc = __dadd_rn(acc, fr.leaf[base + node]);
+        }
+        const JobDev J = jobs[h.job];
+        J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)fr.n_trees);
     }
 }
 
@@ -990,7 +1053,6 @@ struct nlf_forest {
     int *d_off = nullptr;
     long long n_nodes = 0;
     std::vector<int> off;            // host copy of tree offsets
-    std::vector<int> part_begin;     // shared-memory parts: trees [part_begin[p], part_begin[p+1])
 };
 
 struct HostJob {
@@ -1022,6 +1084,7 @@ struct nlf_batch {
     GroupHdr *d_hdr = nullptr;
     float *d_featT = nullptr;
     unsigned *d_group_counter = nullptr;
+    unsigned *d_nanmask = nullptr;
     int *d_overflow = nullptr;
     double *d_exp = nullptr;
     unsigned max_groups = 0;
@@ -1160,53 +1223,28 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
             nodes[(size_t)(b + k)] = nd;
         }
     }
-    // shared-memory format: leaves carry their value in place (needs a clear sign bit); trees are
-    // grouped into parts that fit in shared memory next to FOREST_WARPS feature tiles, and right
-    // children are stored as indices inside their part.
+    // shared-memory format: leaves carry their value in place (needs a clear sign bit); right
+    // children stay tree-local here and are rebased when a kernel stages its part.
     std::vector<uint2> nodes2((size_t)total);
-    std::vector<int> part_begin;
     bool v2_ok = true;
-    {
-        const size_t smem_max = 232448 - 64;              // 227 KB opt-in limit per block on sm_100 (minus static)
-        const size_t feat_bytes = 2 * sizeof(float) * (size_t)n_features * 32;       // two feature tiles
-        if (feat_bytes + 4096 >= smem_max) v2_ok = false;
-        int t = 0;
-        while (t < n_trees && v2_ok) {
-            part_begin.push_back(t);
-            int t1 = t;
-            while (t1 < n_trees) {
-                size_t nn = (size_t)(tree_off[t1 + 1] - tree_off[t]);
-                size_t need = forest_coop_smem(nn, t1 + 1 - t, n_features);
-                if (need > smem_max) break;
-                t1++;
+    for (int t = 0; t < n_trees && v2_ok; t++) {
+        long long b = tree_off[t], cnt = tree_off[t + 1] - b;
+        if (cnt >= (1 << 19)) v2_ok = false;
+        for (long long k = 0; k < cnt && v2_ok; k++) {
+            uint2 nd;
+            if (left[b + k] < 0) {
+                double v = leaf_p1[b + k];
+                if (std::signbit(v)) { v2_ok = false; break; }
+                uint64_t bits;
+                memcpy(&bits, &v, 8);
+                nd.x = (unsigned)(bits & 0xffffffffu);
+                nd.y = (unsigned)(bits >> 32);
+            } else {
+                nd.x = nodes[(size_t)(b + k)].x;
+                nd.y = 0x80000000u | ((unsigned)feature[b + k] << 23) |
+                       ((missing_left && missing_left[b + k]) ? 0x400000u : 0u) | (unsigned)right[b + k];
             }
-            if (t1 == t) v2_ok = false;                   // a single tree does not fit
-            t = t1;
-        }
-        part_begin.push_back(n_trees);
-    }
-    for (size_t p = 0; v2_ok && p + 1 < part_begin.size(); p++) {
-        const long long pbase = tree_off[part_begin[p]];
-        if (tree_off[part_begin[p + 1]] - pbase >= (1 << 22)) v2_ok = false;
-        for (int t = part_begin[p]; t < part_begin[p + 1] && v2_ok; t++) {
-            long long b = tree_off[t], cnt = tree_off[t + 1] - b;
-            for (long long k = 0; k < cnt; k++) {
-                uint2 nd;
-                if (left[b + k] < 0) {
-                    double v = leaf_p1[b + k];
-                    if (std::signbit(v)) { v2_ok = false; break; }
-                    uint64_t bits;
-                    memcpy(&bits, &v, 8);
-                    nd.x = (unsigned)(bits & 0xffffffffu);
-                    nd.y = (unsigned)(bits >> 32);
-                } else {
-                    nd.x = nodes[(size_t)(b + k)].x;
-                    nd.y = 0x80000000u | ((unsigned)feature[b + k] << 23) |
-                           ((missing_left && missing_left[b + k]) ? 0x400000u : 0u) |
-                           (unsigned)(b - pbase + right[b + k]);
-                }
-                nodes2[(size_t)(b + k)] = nd;
-            }
+            nodes2[(size_t)(b + k)] = nd;
         }
     }
     NLF_CUDA(cudaSetDevice(ctx->device));
@@ -1214,7 +1252,6 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
     f->ctx = ctx;
     f->n_nodes = total;
     f->off = off;
-    f->part_begin = part_begin;
     if (v2_ok) {
         NLF_CUDA(cudaMalloc(&f->d_nodes2, sizeof(uint2) * (size_t)total));
         NLF_CUDA(cudaMemcpy(f->d_nodes2, nodes2.data(), sizeof(uint2) * (size_t)total, cudaMemcpyHostToDevice));
@@ -1375,17 +1412,56 @@ static int launch_features(nlf_batch *b, int total_tiles, int nexp)
     KLaunch k(c, P_FEATURE);
     k_features<W><<<total_tiles, FeatCfg<W>::NT, 0, c->stream>>>(
         b->d_jobs, b->d_tile_base, (int)b->jobs.size(), b->lower, b->upper, b->pitch, b->ndp, b->ndt, b->d_exp, nexp,
-        b->d_hdr, b->d_featT, b->d_group_counter, b->max_groups, b->d_overflow);
+        b->d_hdr, b->d_featT, b->d_group_counter, b->max_groups, b->d_overflow, b->d_nanmask);
     return NLF_OK;
+}
+
+// dynamic shared memory of the cooperative forest kernels for a part of `nodes` nodes in `ntree` trees
+static inline size_t forest_dyn_smem(size_t nodes, int ntree, int F)
+{
+    return 2 * (size_t)F * 128 + 2 * (size_t)ntree * 256 + 256 + ((nodes + 2) & ~(size_t)1) * 8 +
+           sizeof(int) * (size_t)((ntree + 1 + 3) & ~3) + 64;
 }
 
 // K8 launch: shared-memory forest parts when they fit, else the global-memory kernel.
 static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
 {
     nlf_ctx *c = b->ctx;
-    const size_t smem_max = 232448;
+    const size_t smem_max = 232448;                            // 227 KB opt-in limit per block on sm_100
     const int T = f->dev.n_trees;
-    if (f->d_nodes2 == nullptr) {
+    bool use_smem = f->d_nodes2 != nullptr;
+    std::vector<int> part_begin;
+    if (use_smem) {
+        // parts of consecutive trees that fit in shared memory, then an even split of the tree count
+        int nparts_needed = 0, t = 0;
+        while (t < T && use_smem) {
+            int t1 = t;
+            while (t1 < T && forest_dyn_smem((size_t)(f->off[t1 + 1] - f->off[t]), t1 + 1 - t, F) <= smem_max - 64) t1++;
+            if (t1 == t) use_smem = false;                     // a single tree does not fit
+            nparts_needed++;
+            t = t1;
+        }
+        if (use_smem) {
+            bool even_ok = true;
+            std::vector<int> even;
+            for (int p = 0; p <= nparts_needed; p++) even.push_back((int)((long long)T * p / nparts_needed));
+            for (int p = 0; p < nparts_needed && even_ok; p++)
+                if (forest_dyn_smem((size_t)(f->off[even[p + 1]] - f->off[even[p]]), even[p + 1] - even[p], F) > smem_max - 64)
+                    even_ok = false;
+            if (even_ok) part_begin = even;
+            else {
+                t = 0;
+                while (t < T) {
+                    part_begin.push_back(t);
+                    int t1 = t;
+                    while (t1 < T && forest_dyn_smem((size_t)(f->off[t1 + 1] - f->off[t]), t1 + 1 - t, F) <= smem_max - 64) t1++;
+                    t = t1;
+                }
+                part_begin.push_back(T);
+            }
+        }
+    }
+    if (!use_smem) {
         constexpr int GW = 4;
         size_t smem = sizeof(float) * (size_t)GW * F * 32;
         NLF_CUDA(cudaFuncSetAttribute(k_forest<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1395,44 +1471,45 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
         NLF_CUDA(cudaGetLastError());
         return NLF_OK;
     }
-    const int nparts = (int)f->part_begin.size() - 1;
-    double *acc = nullptr;
-    if (nparts > 1) NLF_CUDA(cudaMallocAsync(&acc, sizeof(double) * (size_t)b->max_groups * 32, c->stream));
     static int cfg = -1;
     if (cfg < 0) {
-        const char *e = getenv("NLF_FOREST_CFG");              // tuning knob: "<warps>x<ilp>"
-        cfg = 1;
+        const char *e = getenv("NLF_FOREST_CFG");              // tuning knob: pipe32 (default), pipe16, dyn32, dyn16
+        cfg = 0;
         if (e) {
-            if (!strcmp(e, "8x2")) cfg = 0;
-            else if (!strcmp(e, "16x1")) cfg = 1;
-            else if (!strcmp(e, "16x2")) cfg = 2;
-            else if (!strcmp(e, "12x1")) cfg = 3;
-            else if (!strcmp(e, "10x1")) cfg = 4;
-            else if (!strcmp(e, "8x1")) cfg = 5;
+            if (!strcmp(e, "pipe16")) cfg = 1;
+            else if (!strcmp(e, "dyn32")) cfg = 2;
+            else if (!strcmp(e, "dyn16")) cfg = 3;
         }
     }
+    const int nparts = (int)part_begin.size() - 1;
+    double *acc = nullptr;
+    if (nparts > 1) NLF_CUDA(cudaMallocAsync(&acc, sizeof(double) * (size_t)b->max_groups * 32, c->stream));
     for (int p = 0; p < nparts; p++) {
-        int t0 = f->part_begin[p], t1 = f->part_begin[p + 1];
-        size_t nodes = (size_t)(f->off[t1] - f->off[t0]);
-        size_t smem = forest_coop_smem(nodes, t1 - t0, F);
+        int t0 = part_begin[p], t1 = part_begin[p + 1];
+        size_t smem = forest_dyn_smem((size_t)(f->off[t1] - f->off[t0]), t1 - t0, F);
         KLaunch k(c, P_FOREST);
-#define NLF_LAUNCH_COOP(NWv, ILPv)                                                                                  \
+#define NLF_LAUNCH_COOP(KERN, A)                                                                                    \
         do {                                                                                                        \
-            NLF_CUDA(cudaFuncSetAttribute(k_forest_coop<NWv, ILPv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+            NLF_CUDA(cudaFuncSetAttribute(KERN<A>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                           (int)(smem_max - 64)));                                                   \
-            k_forest_coop<NWv, ILPv><<<c->sm_count, 32 * NWv, smem, c->stream>>>(                                   \
-                f->d_nodes2, f->d_off, t0, t1, T, F, b->d_hdr, b->d_featT, b->d_group_counter, b->d_jobs, b->lower, \
-                w, b->ndp, acc, p == 0, p == nparts - 1);                                                           \
+            KERN<A><<<c->sm_count, 32 * A, smem, c->stream>>>(                                                      \
+                f->d_nodes2, f->d_off, t0, t1, T, F, b->d_hdr, b->d_nanmask, b->d_featT, b->d_group_counter,        \
+                b->d_jobs, b->lower, w, b->ndp, acc, p == 0, p == nparts - 1);                                      \
         } while (0)
         switch (cfg) {
-            case 0: NLF_LAUNCH_COOP(8, 2); break;
-            case 2: NLF_LAUNCH_COOP(16, 2); break;
-            case 3: NLF_LAUNCH_COOP(12, 1); break;
-            case 4: NLF_LAUNCH_COOP(10, 1); break;
-            case 5: NLF_LAUNCH_COOP(8, 1); break;
-            default: NLF_LAUNCH_COOP(16, 1); break;
+            case 1: NLF_LAUNCH_COOP(k_forest_pipe, 16); break;
+            case 2: NLF_LAUNCH_COOP(k_forest_dyn, 32); break;
+            case 3: NLF_LAUNCH_COOP(k_forest_dyn, 16); break;
+            default: NLF_LAUNCH_COOP(k_forest_pipe, 32); break;
         }
 #undef NLF_LAUNCH_COOP
+        NLF_CUDA(cudaGetLastError());
+    }
+    {
+        // pixels with NaN features (rare: constant windows) through the general kernel
+        KLaunch k(c, P_FOREST);
+        k_forest_nan<<<c->sm_count * 4, 256, 0, c->stream>>>(f->dev, b->d_hdr, b->d_nanmask, b->d_featT,
+                                                             b->d_group_counter, b->d_jobs, b->lower, w, b->ndp);
         NLF_CUDA(cudaGetLastError());
     }
     if (acc) NLF_CUDA(cudaFreeAsync(acc, c->stream));
@@ -1553,6 +1630,8 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     NLF_CUDA(cudaMallocAsync(&b->d_hdr, sizeof(GroupHdr) * (size_t)groups, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_featT, sizeof(float) * (size_t)groups * F * 32, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned), c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
+    NLF_CUDA(cudaMemsetAsync(b->d_nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_overflow, sizeof(int), c->stream));
     NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
     NLF_CUDA(cudaMemsetAsync(b->d_overflow, 0, sizeof(int), c->stream));
@@ -1810,6 +1889,7 @@ static void free_score_outputs(nlf_batch *b)
     if (b->d_hdr) { cudaFreeAsync(b->d_hdr, s); b->d_hdr = nullptr; }
     if (b->d_featT) { cudaFreeAsync(b->d_featT, s); b->d_featT = nullptr; }
     if (b->d_group_counter) { cudaFreeAsync(b->d_group_counter, s); b->d_group_counter = nullptr; }
+    if (b->d_nanmask) { cudaFreeAsync(b->d_nanmask, s); b->d_nanmask = nullptr; }
     if (b->d_overflow) { cudaFreeAsync(b->d_overflow, s); b->d_overflow = nullptr; }
     if (b->d_exp) { cudaFreeAsync(b->d_exp, s); b->d_exp = nullptr; }
 }
@@ -1907,6 +1987,7 @@ NLF_EXPORT int nlf_batch_destroy(nlf_batch *b)
     if (b->d_hdr) cudaFreeAsync(b->d_hdr, s);
     if (b->d_featT) cudaFreeAsync(b->d_featT, s);
     if (b->d_group_counter) cudaFreeAsync(b->d_group_counter, s);
+    if (b->d_nanmask) cudaFreeAsync(b->d_nanmask, s);
     if (b->d_overflow) cudaFreeAsync(b->d_overflow, s);
     if (b->d_exp) cudaFreeAsync(b->d_exp, s);
     delete b;

@@ -146,3 +146,31 @@ def test_batch_of_all_cases_matches_oracle(gpu, forests, models):
         assert np.array_equal(np.stack([i, j], 1), cl)
         assert np.array_equal(p, pr)
     batch.close()
+
+
+def test_constant_windows_give_nan_features_like_sklearn(gpu, forests, models):
+    """A flat matrix: every window beyond the diagonal zone is constant, so max == min and the
+    min-max normalisation yields NaN features (callers.py:606, util.py:493-497); sklearn >= 1.4
+    routes NaN by missing_go_to_left.  Covers the NaN path of the forest kernels."""
+    from oracle import coracle as co
+    from neoloopfinder_b200.scoring import ScoreBatch
+    n = 96
+    G = np.triu(np.full((n, n), 0.75))
+    G[40:44, 70:75] = 2.5                      # a few non-constant windows too
+    exp = np.ones(501)
+    forest = forests("forest_w6.joblib")
+    model = models("forest_w6.joblib")
+    batch = ScoreBatch(4, 400, gpu)
+    batch.add_dense(G)
+    batch.keep_features(True)
+    batch.score(forest, exp, 0.5)
+    i, j, p = batch.scored(0)
+    fea32 = batch.features32(0)
+    assert np.isnan(fea32).all(axis=1).sum() > 1000          # the constant windows
+    assert (~np.isnan(fea32).any(axis=1)).sum() > 100          # and ordinary ones
+    cl, pr, f32 = co.score_matrix(G, exp, co.sklearn_forest_arrays(model), 6)
+    assert np.array_equal(np.stack([i, j], 1), cl)
+    assert np.array_equal(fea32.view(np.uint32), f32.view(np.uint32))
+    assert np.array_equal(p, pr)
+    assert np.array_equal(p, model.predict_proba(fea32)[:, 1])
+    batch.close()
