@@ -34,21 +34,7 @@ log = logging.getLogger(__name__)
 # ----------------------------------------------------------------------------------------------
 # scoring of assemblies
 # ----------------------------------------------------------------------------------------------
-def estimate_pixels(n_bins: int) -> int:
-    """Upper bound of scored pixels for a gap-free matrix of n bins."""
-    return max(0, 393 * n_bins - 80172) if n_bins >= 401 else max(0, n_bins * (n_bins - 8) // 2)
-
-
-def lpt_shards(weights: List[float], n_shards: int) -> List[List[int]]:
-    """Greedy longest-processing-time partition of item indices into n_shards lists."""
-    order = sorted(range(len(weights)), key=lambda k: (-weights[k], k))
-    loads = [0.0] * n_shards
-    shards = [[] for _ in range(n_shards)]
-    for k in order:
-        s = min(range(n_shards), key=lambda q: (loads[q], q))
-        shards[s].append(k)
-        loads[s] += weights[k]
-    return shards
+from .sharding import assembly_weight, estimate_pixels, lpt_shards  # noqa: E402,F401 (re-exported)
 
 
 def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model, expected, ctx=None,
@@ -124,10 +110,7 @@ def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, 
     ids = list(assemblies)
     res = clr.binsize
     # cost estimate from the assembly geometry only
-    weights = []
-    for ID in ids:
-        nsv = max(1, len(assemblies[ID].split()) - 2)
-        weights.append(float(estimate_pixels(int((2 + 0.5 * (nsv - 1)) * rsize // res))))
+    weights = [assembly_weight(assemblies[ID], rsize, res) for ID in ids]
     shards = lpt_shards(weights, len(devices))
     results: Dict[str, Optional[dict]] = {}
     errors = []
