@@ -190,7 +190,7 @@ template <int W>
 struct FeatCfg {
     static constexpr int S = 2 * W + 1;
     static constexpr int F = S * S;
-    static constexpr int TX = 16;
+    static constexpr int TX = (W >= 7) ? 8 : 16;   // matrix rows per tile (static shared memory stays below 48 KB)
     static constexpr int TR = TX + 2 * W;       // tile rows incl. halo
     static constexpr int TC = 32 + 4 * W;       // tile band columns incl. halo
     static constexpr int VC = 32 + 2 * W;       // columns of the axis-0 result
@@ -217,8 +217,8 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     __shared__ double Et[TR][TC];
     __shared__ unsigned char Hs[TR][TC];
     __shared__ double Vx[S][VC];
-    __shared__ double red_min[S][32];
-    __shared__ double red_max[S][32];
+    __shared__ double red_min[2][S][32];      // double buffered: one block barrier per row
+    __shared__ double red_max[2][S][32];
     __shared__ unsigned passmask[TX];
     __shared__ unsigned s_group_base;
 
@@ -316,6 +316,7 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
 
     // ---- phase 2: rows
     unsigned g = gbase;
+    unsigned rb = 0;                                  // parity of the min/max exchange buffer
     for (int xi = 0; xi < TX; xi++) {
         unsigned pm = passmask[xi];
         if (!pm) continue;
@@ -327,7 +328,7 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
             unsigned mm = mode ? (pm & raw_lanes) : (pm & ~raw_lanes);
             if (!mm) continue;
             const double (*T)[TC] = mode ? Rt : Et;
-            // stage A: axis-0 pass, warp a -> Vx[a][*]
+            // stage A: axis-0 pass, warp a -> Vx[a][*]  (row a is produced and consumed by warp a only)
             {
                 const int a = warp;
                 int ra[9];
@@ -345,11 +346,12 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
                     Vx[a][cc] = v;
                 }
             }
-            __syncthreads();
+            __syncwarp();
             // stage B: axis-1 pass for window row a = warp, window of lane
             double in[S], out[S];
 #pragma unroll
             for (int b = 0; b < S; b++) in[b] = Vx[warp][lane + b];
+            __syncwarp();                              // Vx[warp] may be overwritten by the next stage A
             double rmin, rmax;
             bool has_nan = false;
 #pragma unroll
@@ -368,25 +370,36 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
                 else { rmin = (v < rmin) ? v : rmin; rmax = (v > rmax) ? v : rmax; }
             }
             if (has_nan) { rmin = qnan; rmax = qnan; }
-            red_min[warp][lane] = rmin;
-            red_max[warp][lane] = rmax;
+            red_min[rb][warp][lane] = rmin;
+            red_max[rb][warp][lane] = rmax;
             __syncthreads();
-            double mn = red_min[0][lane], mx = red_max[0][lane];
+            double mn = red_min[rb][0][lane], mx = red_max[rb][0][lane];
             bool nn = (mn != mn);
 #pragma unroll
             for (int a = 1; a < S; a++) {
-                double u = red_min[a][lane], v = red_max[a][lane];
+                double u = red_min[rb][a][lane], v = red_max[rb][a][lane];
                 nn |= (u != u);
                 mn = (u < mn) ? u : mn;
                 mx = (v > mx) ? v : mx;
             }
+            rb ^= 1u;            // the buffer is reused two barriers from now: every warp has read it by then
             if (nn) { mn = qnan; mx = qnan; }
             bool f_nan = false;
             if ((mm >> lane) & 1u) {
-                double den = __dsub_rn(mx, mn);
+                const double den = __dsub_rn(mx, mn);
+                // float32(fl64(num/den)) without 13 fp64 divisions: p = fl64(num * fl64(1/den)) is within
+                // 2.01 ulp64 of the exact quotient, so it rounds to the same float32 unless it sits within
+                // 8 ulp64 of a float32 rounding boundary (low 29 mantissa bits ~ 0x10000000) or in the
+                // float32 subnormal range; those (about 1 in 3e7) take the exact division.
+                const bool fast_ok = (den > 1e-290) && (den < 1e300);
+                const double rden = __ddiv_rn(1.0, fast_ok ? den : 1.0);
 #pragma unroll
                 for (int b = 0; b < S; b++) {
-                    double f = __ddiv_rn(__dsub_rn(out[b], mn), den);
+                    const double num = __dsub_rn(out[b], mn);
+                    double f = __dmul_rn(num, rden);
+                    const unsigned dropped = (unsigned)__double2loint(f) & 0x1fffffffu;
+                    const bool risky = !fast_ok || (dropped - 0x0ffffff8u <= 16u) || (f < 1.2e-38 && f != 0.0);
+                    if (risky) f = __ddiv_rn(num, den);
                     f_nan |= (f != f);
                     fdst[(size_t)(warp * S + b) * 32 + lane] = __double2float_rn(f);
                 }
@@ -397,8 +410,6 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
                 unsigned nb = __ballot_sync(0xffffffffu, f_nan);
                 if (lane == 0 && nb) atomicOr(&nanmask[g], nb);
             }
-            // red_* are rewritten only after the next stage-A barrier; Vx only after this point
-            __syncthreads();
         }
         if (warp == 0 && ((pm >> lane) & 1u)) {
             if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)(g * 32u + lane);
@@ -1521,7 +1532,7 @@ static int upload_jobs(nlf_batch *b, int w)
 {
     nlf_ctx *c = b->ctx;
     const int nj = (int)b->jobs.size();
-    const int TX = 16;
+    const int TX = (w >= 7) ? 8 : 16;                 // FeatCfg<W>::TX
     std::vector<JobDev> jd(nj);
     std::vector<int> tb(nj + 1);
     int tiles = 0;
@@ -1539,7 +1550,6 @@ static int upload_jobs(nlf_batch *b, int w)
         groups += (long long)d.ntx * TX * std::max(1, b->ndt);
     }
     tb[nj] = tiles;
-    (void)w;
     if (!b->d_jobs) {
         NLF_CUDA(cudaMallocAsync(&b->d_jobs, sizeof(JobDev) * nj, c->stream));
         NLF_CUDA(cudaMallocAsync(&b->d_tile_base, sizeof(int) * (nj + 1), c->stream));
