@@ -334,9 +334,15 @@ def main():
         step_e2e()
     barrier()
     ctx.timer_start()
+    t_e2e = time.perf_counter()
     for _ in range(args.steps):
+        t_dbg = time.perf_counter()
         loops_e, counts_e = step_e2e()
+        if os.environ.get("NLF_BENCH_DEBUG"):
+            ctx.sync()
+            print("e2e step %.2f ms" % (1e3 * (time.perf_counter() - t_dbg)), file=sys.stderr)
     ms_e = ctx.timer_stop()
+    wall_e = 1000.0 * (time.perf_counter() - t_e2e)
     barrier()
     ms_e = max_over_ranks(ms_e)
     clocks = sampler.stop(mark0, mark1)
@@ -390,7 +396,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e / args.steps},
+                    "ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fp64": fp64, "kernels": kern_tab,
             "pixels": {"scored_per_step_rank0": scored_per_step, "candidates_per_step_rank0": cand_per_step,

@@ -41,9 +41,11 @@ struct JobDev {
     long long *pava_r;  // [upper+2] scratch
     int *status;        // [0] error code of the job (0 ok)
     unsigned long long *counts;  // [0] candidates, [1] scored, [2] donuts
-    int *don_i, *don_j;           // Donut outputs (capacity don_cap)
+    int *don_job, *don_i, *don_j; // Donut outputs: ONE list per batch (capacity don_cap), tagged by job
     double *don_p, *don_v;
+    unsigned long long *don_count;
     long long don_cap;
+    int job;
     int n;
     int ntx;            // number of x tiles
 };
@@ -205,7 +207,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n)
 }
 
 template <int W>
-__global__ void __launch_bounds__(FeatCfg<W>::NT, 1)
+__global__ void __launch_bounds__(FeatCfg<W>::NT, 2)
 k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int lower, int upper,
            int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, GroupHdr *__restrict__ hdr,
            float *__restrict__ featT, unsigned *__restrict__ group_counter, unsigned max_groups,
@@ -851,9 +853,10 @@ __global__ void k_threshold(const JobDev *__restrict__ jobs, int lower, int uppe
             scored++;
             if (p >= thre) {
                 donuts++;
-                unsigned long long pos = atomicAdd(&J.counts[3], 1ULL);
+                unsigned long long pos = atomicAdd(J.don_count, 1ULL);
                 if ((long long)pos < J.don_cap) {
                     int d = dlo + dd;
+                    J.don_job[pos] = J.job;
                     J.don_i[pos] = x;
                     J.don_j[pos] = x + d;
                     J.don_p[pos] = p;
@@ -1066,20 +1069,12 @@ struct nlf_forest {
     std::vector<int> off;            // host copy of tree offsets
 };
 
+constexpr int NLF_MAX_JOBS = 16384;     // jobs per batch (status / counter pool size)
+
 struct HostJob {
     int n = 0;
-    double *d_dense = nullptr;   // freed after bandify
     double *d_band = nullptr;
-    bool band_owned = true;
-    double *d_prob = nullptr;
-    int *d_slot = nullptr;
-    double *d_means = nullptr, *d_e = nullptr, *d_pw = nullptr;
-    long long *d_pr = nullptr;
-    int *d_status = nullptr;
-    unsigned long long *d_counts = nullptr;
-    int *d_don_i = nullptr, *d_don_j = nullptr;
-    double *d_don_p = nullptr, *d_don_v = nullptr;
-    long long don_cap = 0;
+    size_t prob_off = 0;         // offset (cells) of this job inside the batch's prob / slot pools
     unsigned long long counts[4] = {0, 0, 0, 0};
     int status = 0;
 };
@@ -1090,8 +1085,19 @@ struct nlf_batch {
     int W = 0, ndp = 0, ndt = 0;
     bool keep_slots = false;
     std::vector<HostJob> jobs;
+    // pools: one allocation per batch instead of a dozen per job
+    int *d_status = nullptr;                 // [NLF_MAX_JOBS]
+    unsigned long long *d_counts = nullptr;  // [NLF_MAX_JOBS*4 + 1]; the last word counts the Donuts
+    double *d_scratch = nullptr;             // per job: means, e, pava_w (3 * up1 doubles) and pava_r (up1 int64)
+    int scratch_jobs = 0;
+    double *d_prob = nullptr;
+    int *d_slot = nullptr;
+    int *d_don_job = nullptr, *d_don_i = nullptr, *d_don_j = nullptr;
+    double *d_don_p = nullptr, *d_don_v = nullptr;
+    long long don_cap = 0;
     JobDev *d_jobs = nullptr;
     int *d_tile_base = nullptr;
+    int jobs_cap = 0;
     GroupHdr *d_hdr = nullptr;
     float *d_featT = nullptr;
     unsigned *d_group_counter = nullptr;
@@ -1102,6 +1108,12 @@ struct nlf_batch {
     int total_tiles = 0;
     long long total_groups = 0;
     bool prepared = false, scored = false, counted = false;
+    // host cache of the Donut list (filled by the first fetch after scoring)
+    bool donuts_cached = false;
+    unsigned long long n_donuts_total = 0;
+    std::vector<int> h_don_job, h_don_i, h_don_j;
+    std::vector<double> h_don_p, h_don_v;
+    std::vector<std::vector<int>> don_by_job;
 };
 
 extern int nlf_assembly_export_band(nlf_assembly *a, int bw, int pitch, double **d_band, int *n_out);
@@ -1322,28 +1334,26 @@ NLF_EXPORT int nlf_batch_create(nlf_ctx *ctx, int lower, int upper, nlf_batch **
 {
     if (!ctx || !out) return fail(NLF_ERR_ARG, "nlf_batch_create: NULL argument");
     if (lower < 0 || upper < lower || upper > 4000) return fail(NLF_ERR_ARG, "bad band limits lower=%d upper=%d", lower, upper);
+    NLF_CUDA(cudaSetDevice(ctx->device));
     nlf_batch *b = new nlf_batch();
     b->ctx = ctx;
     b->lower = lower;
     b->upper = upper;
     b->bw = upper + 14;
     b->pitch = round_up(b->bw, 4);
+    cudaStream_t s = ctx->stream;
+    NLF_CUDA(cudaMallocAsync(&b->d_status, sizeof(int) * NLF_MAX_JOBS, s));
+    NLF_CUDA(cudaMallocAsync(&b->d_counts, sizeof(unsigned long long) * (NLF_MAX_JOBS * 4 + 1), s));
+    NLF_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * NLF_MAX_JOBS, s));
+    NLF_CUDA(cudaMemsetAsync(b->d_counts, 0, sizeof(unsigned long long) * (NLF_MAX_JOBS * 4 + 1), s));
     *out = b;
     return NLF_OK;
 }
 
-static int alloc_job_common(nlf_batch *b, HostJob &j)
+static int check_can_add(nlf_batch *b)
 {
-    nlf_ctx *c = b->ctx;
-    int up1 = b->upper + 2;
-    NLF_CUDA(cudaMallocAsync(&j.d_means, sizeof(double) * up1, c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_e, sizeof(double) * up1, c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_pw, sizeof(double) * up1, c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_pr, sizeof(long long) * up1, c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_status, sizeof(int), c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_counts, sizeof(unsigned long long) * 4, c->stream));
-    NLF_CUDA(cudaMemsetAsync(j.d_status, 0, sizeof(int), c->stream));
-    NLF_CUDA(cudaMemsetAsync(j.d_counts, 0, sizeof(unsigned long long) * 4, c->stream));
+    if (b->scored || b->prepared) return fail(NLF_ERR_STATE, "batch already prepared/scored: add matrices first");
+    if ((int)b->jobs.size() >= NLF_MAX_JOBS) return fail(NLF_ERR_ARG, "more than %d matrices in one batch", NLF_MAX_JOBS);
     return NLF_OK;
 }
 
@@ -1351,24 +1361,23 @@ NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
 {
     if (!b || !G || n <= 0) return fail(NLF_ERR_ARG, "nlf_batch_add_dense: bad arguments");
     if (n > 65535) return fail(NLF_ERR_ARG, "dense input limited to n <= 65535 (use the band input), got %d", n);
-    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    int rc = check_can_add(b);
+    if (rc) return rc;
     nlf_ctx *c = b->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
     HostJob j;
     j.n = n;
-    int rc = alloc_job_common(b, j);
-    if (rc) return rc;
-    NLF_CUDA(cudaMallocAsync(&j.d_dense, sizeof(double) * (size_t)n * n, c->stream));
+    double *d_dense;
+    NLF_CUDA(cudaMallocAsync(&d_dense, sizeof(double) * (size_t)n * n, c->stream));
     NLF_CUDA(cudaMallocAsync(&j.d_band, sizeof(double) * (size_t)n * b->pitch, c->stream));
-    NLF_CUDA(cudaMemcpyAsync(j.d_dense, G, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(d_dense, G, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
     {
         KLaunch k(c, P_BANDIFY);
         dim3 grid((b->pitch + 127) / 128, n);
-        k_bandify<<<grid, 128, 0, c->stream>>>(j.d_dense, n, b->bw, b->pitch, j.d_band, j.d_status);
+        k_bandify<<<grid, 128, 0, c->stream>>>(d_dense, n, b->bw, b->pitch, j.d_band, b->d_status + b->jobs.size());
     }
     NLF_CUDA(cudaGetLastError());
-    NLF_CUDA(cudaFreeAsync(j.d_dense, c->stream));
-    j.d_dense = nullptr;
+    NLF_CUDA(cudaFreeAsync(d_dense, c->stream));
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
 }
@@ -1377,13 +1386,12 @@ NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int p
 {
     if (!b || !band || n <= 0 || pitch <= 0) return fail(NLF_ERR_ARG, "nlf_batch_add_band: bad arguments");
     if (n > 65535) return fail(NLF_ERR_ARG, "band input limited to n <= 65535 rows per job, got %d (shard the chromosome)", n);
-    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    int rc = check_can_add(b);
+    if (rc) return rc;
     nlf_ctx *c = b->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
     HostJob j;
     j.n = n;
-    int rc = alloc_job_common(b, j);
-    if (rc) return rc;
     double *d_src;
     NLF_CUDA(cudaMallocAsync(&d_src, sizeof(double) * (size_t)n * pitch, c->stream));
     NLF_CUDA(cudaMallocAsync(&j.d_band, sizeof(double) * (size_t)n * b->pitch, c->stream));
@@ -1402,13 +1410,12 @@ NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int p
 NLF_EXPORT int nlf_batch_add_assembly(nlf_batch *b, nlf_assembly *a)
 {
     if (!b || !a) return fail(NLF_ERR_ARG, "nlf_batch_add_assembly: NULL argument");
-    if (b->scored) return fail(NLF_ERR_STATE, "batch already scored");
+    int rc = check_can_add(b);
+    if (rc) return rc;
     nlf_ctx *c = b->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
     HostJob j;
-    int rc = nlf_assembly_export_band(a, b->bw, b->pitch, &j.d_band, &j.n);
-    if (rc) return rc;
-    rc = alloc_job_common(b, j);
+    rc = nlf_assembly_export_band(a, b->bw, b->pitch, &j.d_band, &j.n);
     if (rc) return rc;
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
@@ -1527,12 +1534,13 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
     return NLF_OK;
 }
 
-// upload the per-job descriptors (pointers that are still NULL stay NULL)
+// upload the per-job descriptors (pointers into the batch pools; NULL pools stay NULL)
 static int upload_jobs(nlf_batch *b, int w)
 {
     nlf_ctx *c = b->ctx;
     const int nj = (int)b->jobs.size();
     const int TX = (w >= 7) ? 8 : 16;                 // FeatCfg<W>::TX
+    const int up1 = b->upper + 2;
     std::vector<JobDev> jd(nj);
     std::vector<int> tb(nj + 1);
     int tiles = 0;
@@ -1540,9 +1548,18 @@ static int upload_jobs(nlf_batch *b, int w)
     for (int k = 0; k < nj; k++) {
         HostJob &j = b->jobs[k];
         JobDev &d = jd[k];
-        d.band = j.d_band; d.prob = j.d_prob; d.slot = j.d_slot; d.means = j.d_means; d.e = j.d_e;
-        d.pava_w = j.d_pw; d.pava_r = j.d_pr; d.status = j.d_status; d.counts = j.d_counts;
-        d.don_i = j.d_don_i; d.don_j = j.d_don_j; d.don_p = j.d_don_p; d.don_v = j.d_don_v; d.don_cap = j.don_cap;
+        double *sc = b->d_scratch + (size_t)k * 4 * up1;
+        d.band = j.d_band;
+        d.prob = b->d_prob ? b->d_prob + j.prob_off : nullptr;
+        d.slot = b->d_slot ? b->d_slot + j.prob_off : nullptr;
+        d.means = sc; d.e = sc + up1; d.pava_w = sc + 2 * up1;
+        d.pava_r = reinterpret_cast<long long *>(sc + 3 * up1);
+        d.status = b->d_status + k;
+        d.counts = b->d_counts + (size_t)k * 4;
+        d.don_job = b->d_don_job; d.don_i = b->d_don_i; d.don_j = b->d_don_j; d.don_p = b->d_don_p; d.don_v = b->d_don_v;
+        d.don_count = b->d_counts + (size_t)NLF_MAX_JOBS * 4;
+        d.don_cap = b->don_cap;
+        d.job = k;
         d.n = j.n;
         d.ntx = (j.n + TX - 1) / TX;
         tb[k] = tiles;
@@ -1550,9 +1567,11 @@ static int upload_jobs(nlf_batch *b, int w)
         groups += (long long)d.ntx * TX * std::max(1, b->ndt);
     }
     tb[nj] = tiles;
-    if (!b->d_jobs) {
+    if (b->jobs_cap < nj) {
+        if (b->d_jobs) { cudaFreeAsync(b->d_jobs, c->stream); cudaFreeAsync(b->d_tile_base, c->stream); }
         NLF_CUDA(cudaMallocAsync(&b->d_jobs, sizeof(JobDev) * nj, c->stream));
         NLF_CUDA(cudaMallocAsync(&b->d_tile_base, sizeof(int) * (nj + 1), c->stream));
+        b->jobs_cap = nj;
     }
     // pageable sources: the copies are staged before these calls return
     NLF_CUDA(cudaMemcpyAsync(b->d_jobs, jd.data(), sizeof(JobDev) * nj, cudaMemcpyHostToDevice, c->stream));
@@ -1569,6 +1588,11 @@ static int batch_prepare(nlf_batch *b)
     nlf_ctx *c = b->ctx;
     const int nj = (int)b->jobs.size();
     if (nj == 0) { b->prepared = true; return NLF_OK; }
+    if (b->scratch_jobs < nj) {
+        if (b->d_scratch) cudaFreeAsync(b->d_scratch, c->stream);
+        NLF_CUDA(cudaMallocAsync(&b->d_scratch, sizeof(double) * (size_t)nj * 4 * (b->upper + 2), c->stream));
+        b->scratch_jobs = nj;
+    }
     int rc = upload_jobs(b, 0);
     if (rc) return rc;
     {
@@ -1599,7 +1623,6 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     if (w != 5 && w != 6 && w != 7) return fail(NLF_ERR_ARG, "window half-size w=%d not supported (5, 6, 7)", w);
     if (f->dev.n_features != (2 * w + 1) * (2 * w + 1))
         return fail(NLF_ERR_ARG, "forest has %d features, window w=%d needs %d", f->dev.n_features, w, (2 * w + 1) * (2 * w + 1));
-    if (2 * w >= 14) { /* band keeps upper+13 diagonals: enough for w <= 6; w = 7 needs upper+14 */ }
     if (nexp <= 0) return fail(NLF_ERR_ARG, "empty expected array");
     nlf_ctx *c = b->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
@@ -1618,19 +1641,22 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     NLF_CUDA(cudaMallocAsync(&b->d_exp, sizeof(double) * nexp, c->stream));
     NLF_CUDA(cudaMemcpyAsync(b->d_exp, expected, sizeof(double) * nexp, cudaMemcpyHostToDevice, c->stream));
 
+    size_t cells = 0;
+    long long band_cells = 0;
     for (int k = 0; k < nj; k++) {
         HostJob &j = b->jobs[k];
-        size_t cells = (size_t)j.n * b->ndp;
-        NLF_CUDA(cudaMallocAsync(&j.d_prob, sizeof(double) * cells, c->stream));
-        if (b->keep_slots) NLF_CUDA(cudaMallocAsync(&j.d_slot, sizeof(int) * cells, c->stream));
-        j.don_cap = (long long)j.n * (b->upper - dlo + 1);
-        if (j.don_cap > (1LL << 22)) j.don_cap = (1LL << 22);
-        if (j.don_cap < 1) j.don_cap = 1;
-        NLF_CUDA(cudaMallocAsync(&j.d_don_i, sizeof(int) * j.don_cap, c->stream));
-        NLF_CUDA(cudaMallocAsync(&j.d_don_j, sizeof(int) * j.don_cap, c->stream));
-        NLF_CUDA(cudaMallocAsync(&j.d_don_p, sizeof(double) * j.don_cap, c->stream));
-        NLF_CUDA(cudaMallocAsync(&j.d_don_v, sizeof(double) * j.don_cap, c->stream));
+        j.prob_off = cells;
+        cells += (size_t)j.n * b->ndp;
+        band_cells += (long long)j.n * (b->upper - dlo + 1);
     }
+    NLF_CUDA(cudaMallocAsync(&b->d_prob, sizeof(double) * cells, c->stream));
+    if (b->keep_slots) NLF_CUDA(cudaMallocAsync(&b->d_slot, sizeof(int) * cells, c->stream));
+    b->don_cap = std::max(1LL, std::min(band_cells, 1LL << 23));
+    NLF_CUDA(cudaMallocAsync(&b->d_don_job, sizeof(int) * b->don_cap, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_don_i, sizeof(int) * b->don_cap, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_don_j, sizeof(int) * b->don_cap, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_don_p, sizeof(double) * b->don_cap, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_don_v, sizeof(double) * b->don_cap, c->stream));
     rc = upload_jobs(b, w);
     if (rc) return rc;
     const long long groups = b->total_groups;
@@ -1660,6 +1686,7 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     NLF_CUDA(cudaGetLastError());
     b->scored = true;
     b->counted = false;
+    b->donuts_cached = false;
     return NLF_OK;
 }
 
@@ -1672,15 +1699,25 @@ static int batch_sync_counts(nlf_batch *b)
     if (b->counted) return NLF_OK;
     nlf_ctx *c = b->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
-    for (auto &j : b->jobs) {
-        NLF_CUDA(cudaMemcpyAsync(j.counts, j.d_counts, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, c->stream));
-        NLF_CUDA(cudaMemcpyAsync(&j.status, j.d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    const int nj = (int)b->jobs.size();
+    std::vector<unsigned long long> cnt((size_t)nj * 4 + 1, 0ULL);
+    std::vector<int> st(std::max(1, nj), 0);
+    if (nj) {
+        NLF_CUDA(cudaMemcpyAsync(cnt.data(), b->d_counts, sizeof(unsigned long long) * (size_t)nj * 4, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaMemcpyAsync(st.data(), b->d_status, sizeof(int) * nj, cudaMemcpyDeviceToHost, c->stream));
     }
+    NLF_CUDA(cudaMemcpyAsync(&cnt[(size_t)nj * 4], b->d_counts + (size_t)NLF_MAX_JOBS * 4, sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, c->stream));
     int overflow = 0;
     if (b->d_overflow)
         NLF_CUDA(cudaMemcpyAsync(&overflow, b->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     NLF_CUDA(cudaStreamSynchronize(c->stream));
     if (overflow) return fail(NLF_ERR_CUDA, "feature group buffer overflow (internal sizing error)");
+    for (int k = 0; k < nj; k++) {
+        memcpy(b->jobs[k].counts, &cnt[(size_t)k * 4], sizeof(unsigned long long) * 4);
+        b->jobs[k].status = st[k];
+    }
+    b->n_donuts_total = cnt[(size_t)nj * 4];
     b->counted = true;
     return NLF_OK;
 }
@@ -1696,15 +1733,36 @@ NLF_EXPORT int nlf_batch_counts(nlf_batch *b, long long *n_cand, long long *n_sc
         if (n_cand) n_cand[k] = j.status ? -1 : (long long)j.counts[0];
         if (n_scored) n_scored[k] = j.status ? -1 : (long long)j.counts[1];
         if (n_donuts) n_donuts[k] = j.status ? -1 : (long long)j.counts[2];
-        if (!j.status && (long long)j.counts[2] > j.don_cap)
-            return fail(NLF_ERR_ARG, "job %zu: %llu pixels above the threshold exceed the Donut capacity %lld; raise the threshold",
-                        k, j.counts[2], j.don_cap);
     }
+    if (b->scored && (long long)b->n_donuts_total > b->don_cap)
+        return fail(NLF_ERR_ARG, "%llu pixels above the threshold exceed the Donut capacity %lld of the batch; raise the threshold or split the batch",
+                    b->n_donuts_total, b->don_cap);
     if (first_err == NLF_ERR_EMPTY_FIT)
         return fail(NLF_ERR_EMPTY_FIT, "a matrix has no diagonal longer than 5 bins: the isotonic fit of get_candidates is empty");
     if (first_err == NLF_ERR_LOWER_TRI)
         return fail(NLF_ERR_LOWER_TRI, "a matrix has non-zero entries below the main diagonal (np.triu input expected)");
     if (first_err) return fail(first_err, "job failed with status %d", first_err);
+    return NLF_OK;
+}
+
+// one device-to-host copy of the whole Donut list, binned by job on the host
+static int cache_donuts(nlf_batch *b)
+{
+    if (b->donuts_cached) return NLF_OK;
+    nlf_ctx *c = b->ctx;
+    const size_t m = (size_t)std::min<unsigned long long>(b->n_donuts_total, (unsigned long long)b->don_cap);
+    b->h_don_job.resize(m); b->h_don_i.resize(m); b->h_don_j.resize(m); b->h_don_p.resize(m); b->h_don_v.resize(m);
+    if (m) {
+        NLF_CUDA(cudaMemcpyAsync(b->h_don_job.data(), b->d_don_job, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaMemcpyAsync(b->h_don_i.data(), b->d_don_i, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaMemcpyAsync(b->h_don_j.data(), b->d_don_j, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaMemcpyAsync(b->h_don_p.data(), b->d_don_p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaMemcpyAsync(b->h_don_v.data(), b->d_don_v, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+        NLF_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    b->don_by_job.assign(b->jobs.size(), std::vector<int>());
+    for (size_t k = 0; k < m; k++) b->don_by_job[(size_t)b->h_don_job[k]].push_back((int)k);
+    b->donuts_cached = true;
     return NLF_OK;
 }
 
@@ -1716,14 +1774,16 @@ NLF_EXPORT int nlf_batch_fetch_donuts(nlf_batch *b, int job, int *i, int *j, dou
     if (job < 0 || job >= (int)b->jobs.size()) return fail(NLF_ERR_ARG, "job %d out of range", job);
     HostJob &J = b->jobs[job];
     if (J.status) return fail(J.status, "job %d failed with status %d", job, J.status);
-    size_t m = (size_t)J.counts[2];
-    if (m == 0) return NLF_OK;
-    nlf_ctx *c = b->ctx;
-    NLF_CUDA(cudaMemcpyAsync(i, J.d_don_i, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
-    NLF_CUDA(cudaMemcpyAsync(j, J.d_don_j, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
-    NLF_CUDA(cudaMemcpyAsync(prob, J.d_don_p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
-    NLF_CUDA(cudaMemcpyAsync(value, J.d_don_v, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
-    NLF_CUDA(cudaStreamSynchronize(c->stream));
+    if ((long long)b->n_donuts_total > b->don_cap) return fail(NLF_ERR_ARG, "Donut capacity exceeded");
+    rc = cache_donuts(b);
+    if (rc) return rc;
+    const std::vector<int> &idx = b->don_by_job[(size_t)job];
+    for (size_t k = 0; k < idx.size(); k++) {
+        i[k] = b->h_don_i[idx[k]];
+        j[k] = b->h_don_j[idx[k]];
+        prob[k] = b->h_don_p[idx[k]];
+        value[k] = b->h_don_v[idx[k]];
+    }
     return NLF_OK;
 }
 
@@ -1740,7 +1800,9 @@ static int ordered_list(nlf_batch *b, int job, int mode, long long cap, int *oi,
     const int nd = b->upper - b->lower + 1;
     JobDev d;
     memset(&d, 0, sizeof(d));
-    d.band = J.d_band; d.prob = J.d_prob; d.slot = J.d_slot; d.e = J.d_e; d.n = J.n; d.status = J.d_status;
+    d.band = J.d_band; d.prob = b->d_prob ? b->d_prob + J.prob_off : nullptr;
+    d.slot = b->d_slot ? b->d_slot + J.prob_off : nullptr;
+    d.e = b->d_scratch + (size_t)job * 4 * (b->upper + 2) + (b->upper + 2); d.n = J.n; d.status = b->d_status + job;
     int *d_cnt;
     long long *d_off;
     NLF_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * nd, c->stream));
@@ -1888,20 +1950,10 @@ NLF_EXPORT int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const i
 static void free_score_outputs(nlf_batch *b)
 {
     cudaStream_t s = b->ctx->stream;
-    for (auto &j : b->jobs) {
-        if (j.d_prob) { cudaFreeAsync(j.d_prob, s); j.d_prob = nullptr; }
-        if (j.d_slot) { cudaFreeAsync(j.d_slot, s); j.d_slot = nullptr; }
-        if (j.d_don_i) {
-            cudaFreeAsync(j.d_don_i, s); cudaFreeAsync(j.d_don_j, s); cudaFreeAsync(j.d_don_p, s); cudaFreeAsync(j.d_don_v, s);
-            j.d_don_i = j.d_don_j = nullptr; j.d_don_p = j.d_don_v = nullptr;
-        }
-    }
-    if (b->d_hdr) { cudaFreeAsync(b->d_hdr, s); b->d_hdr = nullptr; }
-    if (b->d_featT) { cudaFreeAsync(b->d_featT, s); b->d_featT = nullptr; }
-    if (b->d_group_counter) { cudaFreeAsync(b->d_group_counter, s); b->d_group_counter = nullptr; }
-    if (b->d_nanmask) { cudaFreeAsync(b->d_nanmask, s); b->d_nanmask = nullptr; }
-    if (b->d_overflow) { cudaFreeAsync(b->d_overflow, s); b->d_overflow = nullptr; }
-    if (b->d_exp) { cudaFreeAsync(b->d_exp, s); b->d_exp = nullptr; }
+    auto fr = [&](auto *&p) { if (p) { cudaFreeAsync(p, s); p = nullptr; } };
+    fr(b->d_prob); fr(b->d_slot);
+    fr(b->d_don_job); fr(b->d_don_i); fr(b->d_don_j); fr(b->d_don_p); fr(b->d_don_v);
+    fr(b->d_hdr); fr(b->d_featT); fr(b->d_group_counter); fr(b->d_nanmask); fr(b->d_overflow); fr(b->d_exp);
 }
 
 // Forget the results of a scored batch but keep the matrices resident in HBM, so that the
@@ -1912,13 +1964,20 @@ NLF_EXPORT int nlf_batch_reset(nlf_batch *b)
     nlf_ctx *c = b->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
     free_score_outputs(b);
-    for (auto &j : b->jobs) {
-        NLF_CUDA(cudaMemsetAsync(j.d_counts, 0, sizeof(unsigned long long) * 4, c->stream));
-        int keep = (j.status == NLF_ERR_LOWER_TRI) ? NLF_ERR_LOWER_TRI : 0;
-        NLF_CUDA(cudaMemcpyAsync(j.d_status, &keep, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        memset(j.counts, 0, sizeof(j.counts));
+    const int nj = (int)b->jobs.size();
+    if (nj) {
+        // keep the statuses the input stage raised (lower-triangular input); the fit status is recomputed
+        std::vector<int> st(nj);
+        for (int k = 0; k < nj; k++) {
+            st[k] = (b->jobs[k].status == NLF_ERR_LOWER_TRI) ? NLF_ERR_LOWER_TRI : 0;
+            memset(b->jobs[k].counts, 0, sizeof(b->jobs[k].counts));
+        }
+        if (b->counted) NLF_CUDA(cudaMemcpyAsync(b->d_status, st.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, c->stream));
+        NLF_CUDA(cudaMemsetAsync(b->d_counts, 0, sizeof(unsigned long long) * (size_t)nj * 4, c->stream));
     }
+    NLF_CUDA(cudaMemsetAsync(b->d_counts + (size_t)NLF_MAX_JOBS * 4, 0, sizeof(unsigned long long), c->stream));
     b->prepared = b->scored = b->counted = false;
+    b->donuts_cached = false;
     return NLF_OK;
 }
 
@@ -1984,22 +2043,14 @@ NLF_EXPORT int nlf_batch_destroy(nlf_batch *b)
     nlf_ctx *c = b->ctx;
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
-    for (auto &j : b->jobs) {
-        if (j.d_band && j.band_owned) cudaFreeAsync(j.d_band, s);
-        if (j.d_prob) cudaFreeAsync(j.d_prob, s);
-        if (j.d_slot) cudaFreeAsync(j.d_slot, s);
-        cudaFreeAsync(j.d_means, s); cudaFreeAsync(j.d_e, s); cudaFreeAsync(j.d_pw, s); cudaFreeAsync(j.d_pr, s);
-        cudaFreeAsync(j.d_status, s); cudaFreeAsync(j.d_counts, s);
-        if (j.d_don_i) { cudaFreeAsync(j.d_don_i, s); cudaFreeAsync(j.d_don_j, s); cudaFreeAsync(j.d_don_p, s); cudaFreeAsync(j.d_don_v, s); }
-    }
+    free_score_outputs(b);
+    for (auto &j : b->jobs)
+        if (j.d_band) cudaFreeAsync(j.d_band, s);
+    if (b->d_status) cudaFreeAsync(b->d_status, s);
+    if (b->d_counts) cudaFreeAsync(b->d_counts, s);
+    if (b->d_scratch) cudaFreeAsync(b->d_scratch, s);
     if (b->d_jobs) cudaFreeAsync(b->d_jobs, s);
     if (b->d_tile_base) cudaFreeAsync(b->d_tile_base, s);
-    if (b->d_hdr) cudaFreeAsync(b->d_hdr, s);
-    if (b->d_featT) cudaFreeAsync(b->d_featT, s);
-    if (b->d_group_counter) cudaFreeAsync(b->d_group_counter, s);
-    if (b->d_nanmask) cudaFreeAsync(b->d_nanmask, s);
-    if (b->d_overflow) cudaFreeAsync(b->d_overflow, s);
-    if (b->d_exp) cudaFreeAsync(b->d_exp, s);
     delete b;
     return NLF_OK;
 }
