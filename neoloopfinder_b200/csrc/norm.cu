@@ -17,7 +17,7 @@ struct nlf_assembly {
     nlf_ctx *ctx = nullptr;
     int n = 0, nblk = 0;
     double *d_M = nullptr, *d_bias = nullptr, *d_val = nullptr;
-    int *d_blk = nullptr, *d_op = nullptr, *d_kept = nullptr;
+    int *d_blk = nullptr, *d_op = nullptr, *d_kept = nullptr, *d_blo = nullptr, *d_bhi = nullptr;
     std::vector<int> blo, bhi, kept;
     bool scales_set = false, gaps_done = false;
 };
@@ -79,22 +79,35 @@ __global__ void k_pair_means(const double *__restrict__ scratch, size_t stride, 
 }
 
 // K4a: column sums of hcm in numpy's axis-0 order (row after row), one thread per column.
+// The rescale rule only changes at block boundaries, so the loop runs block by block with the
+// rule in registers and eight independent loads in flight; the additions stay strictly sequential.
 __global__ void k_gap_columns(const double *__restrict__ M, int n, const int *__restrict__ blk,
+                              const int *__restrict__ blo, const int *__restrict__ bhi,
                               const int *__restrict__ op, const double *__restrict__ val, int nblk,
                               unsigned char *__restrict__ is_gap)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    double s = scaled_value(M, n, blk, op, val, nblk, 0, j);
-    int r = 1;
-    for (; r + 4 <= n; r += 4) {
-        double a0 = scaled_value(M, n, blk, op, val, nblk, r, j);
-        double a1 = scaled_value(M, n, blk, op, val, nblk, r + 1, j);
-        double a2 = scaled_value(M, n, blk, op, val, nblk, r + 2, j);
-        double a3 = scaled_value(M, n, blk, op, val, nblk, r + 3, j);
-        s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, a0), a1), a2), a3);
+    const int bj = blk[j];
+    double s = 0.0;
+    bool first = true;
+    for (int b = 0; b < nblk; b++) {
+        const int o = op[b * nblk + bj];
+        const double v = val[b * nblk + bj];
+        int r = blo[b];
+        const int re = bhi[b];
+        const double *col = M + j;
+        auto sc = [&](double a) { return (o == 1) ? __ddiv_rn(a, v) : (o == 2) ? __dmul_rn(a, v) : a; };
+        if (first && r < re) { s = sc(col[(size_t)r * n]); r++; first = false; }     // out[j] starts as M[0][j]
+        for (; r + 8 <= re; r += 8) {
+            double a0 = col[(size_t)(r + 0) * n], a1 = col[(size_t)(r + 1) * n], a2 = col[(size_t)(r + 2) * n],
+                   a3 = col[(size_t)(r + 3) * n], a4 = col[(size_t)(r + 4) * n], a5 = col[(size_t)(r + 5) * n],
+                   a6 = col[(size_t)(r + 6) * n], a7 = col[(size_t)(r + 7) * n];
+            s = __dadd_rn(s, sc(a0)); s = __dadd_rn(s, sc(a1)); s = __dadd_rn(s, sc(a2)); s = __dadd_rn(s, sc(a3));
+            s = __dadd_rn(s, sc(a4)); s = __dadd_rn(s, sc(a5)); s = __dadd_rn(s, sc(a6)); s = __dadd_rn(s, sc(a7));
+        }
+        for (; r < re; r++) s = __dadd_rn(s, sc(col[(size_t)r * n]));
     }
-    for (; r < n; r++) s = __dadd_rn(s, scaled_value(M, n, blk, op, val, nblk, r, j));
     is_gap[j] = (s == 0) ? 1 : 0;
 }
 
@@ -140,6 +153,9 @@ NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const d
     }
     for (int r = 0; r < n; r++)
         if (blk[r] < 0) return fail(NLF_ERR_ARG, "bin %d belongs to no block", r);
+    for (int b = 0; b < nblk; b++)
+        if (blk_lo[b] != (b ? blk_hi[b - 1] : 0))
+            return fail(NLF_ERR_ARG, "blocks must tile [0,%d) in ascending order (block %d starts at %d)", n, b, blk_lo[b]);
     NLF_CUDA(cudaSetDevice(ctx->device));
     nlf_assembly *a = new nlf_assembly();
     a->ctx = ctx; a->n = n; a->nblk = nblk;
@@ -152,6 +168,10 @@ NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const d
     NLF_CUDA(cudaMallocAsync(&a->d_op, sizeof(int) * nblk * nblk, s));
     NLF_CUDA(cudaMallocAsync(&a->d_val, sizeof(double) * nblk * nblk, s));
     NLF_CUDA(cudaMallocAsync(&a->d_kept, sizeof(int) * n, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_blo, sizeof(int) * nblk, s));
+    NLF_CUDA(cudaMallocAsync(&a->d_bhi, sizeof(int) * nblk, s));
+    NLF_CUDA(cudaMemcpyAsync(a->d_blo, blk_lo, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(a->d_bhi, blk_hi, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(a->d_M, M, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(a->d_blk, blk.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
@@ -235,7 +255,7 @@ static int ensure_gaps(nlf_assembly *a)
     NLF_CUDA(cudaMallocAsync(&d_gap, n, s));
     {
         KLaunch k(c, P_NORM);
-        k_gap_columns<<<(n + 63) / 64, 64, 0, s>>>(a->d_M, n, a->d_blk, a->d_op, a->d_val, a->nblk, d_gap);
+        k_gap_columns<<<(n + 31) / 32, 32, 0, s>>>(a->d_M, n, a->d_blk, a->d_blo, a->d_bhi, a->d_op, a->d_val, a->nblk, d_gap);
     }
     NLF_CUDA(cudaGetLastError());
     std::vector<unsigned char> gap(n);
@@ -333,6 +353,7 @@ NLF_EXPORT int nlf_assembly_destroy(nlf_assembly *a)
     cudaStream_t s = a->ctx->stream;
     cudaFreeAsync(a->d_M, s); cudaFreeAsync(a->d_bias, s); cudaFreeAsync(a->d_blk, s);
     cudaFreeAsync(a->d_op, s); cudaFreeAsync(a->d_val, s); cudaFreeAsync(a->d_kept, s);
+    cudaFreeAsync(a->d_blo, s); cudaFreeAsync(a->d_bhi, s);
     delete a;
     return NLF_OK;
 }

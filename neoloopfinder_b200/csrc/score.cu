@@ -27,9 +27,11 @@ using namespace nlf;
 //   slot  [n][ndp]    int32  feature slot (group*32+lane) of a scored pixel, -1 otherwise (optional)
 //   e     [upper+1]   fp64   isotonic expected of Peakachu.get_candidates
 // feature groups (shared by all jobs of a chunk)
-//   featT [group][F][32] fp32  features of up to 32 pixels of one matrix row, feature-major so
-//                              that the forest kernel's per-lane column is bank-conflict free
-//   hdr   [group]              {job, x, d0, lane mask}
+//   featT [group][F][32] fp32  features of 32 scored pixels (slots group*32 .. +31, densely packed in
+//                              the order the feature kernel's tiles claim them), feature-major so that
+//                              the forest kernel's per-lane column is bank-conflict free
+//   pix   [slot]               {job, (x << 16) | d} of the pixel in that slot
+//   nanmask [group]            bit l set: slot group*32+l has NaN features
 // ---------------------------------------------------------------------------------------------
 struct JobDev {
     const double *band;
@@ -50,10 +52,8 @@ struct JobDev {
     int ntx;            // number of x tiles
 };
 
-struct GroupHdr {
-    int job, x, d0;
-    unsigned mask;
-};
+// pixel behind feature slot s: .x = job, .y = (matrix row x << 16) | diagonal d
+typedef uint2 PixRef;
 
 __constant__ double c_gw[16];   // gaussian weights, radius 4: c_gw[0..8]
 
@@ -209,8 +209,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n)
 template <int W>
 __global__ void __launch_bounds__(FeatCfg<W>::NT, 2)
 k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int lower, int upper,
-           int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, GroupHdr *__restrict__ hdr,
-           float *__restrict__ featT, unsigned *__restrict__ group_counter, unsigned max_groups,
+           int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, PixRef *__restrict__ pix,
+           float *__restrict__ featT, unsigned *__restrict__ slot_counter, unsigned max_slots,
            int *__restrict__ overflow, unsigned *__restrict__ nanmask)
 {
     using C = FeatCfg<W>;
@@ -222,7 +222,8 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     __shared__ double red_min[2][S][32];      // double buffered: one block barrier per row
     __shared__ double red_max[2][S][32];
     __shared__ unsigned passmask[TX];
-    __shared__ unsigned s_group_base;
+    __shared__ unsigned s_rowbase[TX];       // first feature slot of every tile row
+    __shared__ unsigned s_slots_ok;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- tile -> (job, x0, d0)
@@ -299,15 +300,17 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     }
     __syncthreads();
     if (tid == 0) {
-        int cnt = 0;
-        for (int xi = 0; xi < TX; xi++) cnt += (passmask[xi] != 0);
-        unsigned base = cnt ? atomicAdd(group_counter, (unsigned)cnt) : 0u;
-        if (cnt && base + cnt > max_groups) { atomicExch(overflow, 1); base = 0xffffffffu; }
-        s_group_base = base;
+        // claim one contiguous range of feature slots for the whole tile (one atomic per tile)
+        unsigned cnt = 0;
+        for (int xi = 0; xi < TX; xi++) cnt += __popc(passmask[xi]);
+        unsigned base = cnt ? atomicAdd(slot_counter, cnt) : 0u;
+        unsigned ok = 1u;
+        if (cnt && (base + cnt > max_slots || base + cnt < base)) { atomicExch(overflow, 1); ok = 0u; }
+        for (int xi = 0; xi < TX; xi++) { s_rowbase[xi] = base; base += __popc(passmask[xi]); }
+        s_slots_ok = ok;
     }
     __syncthreads();
-    unsigned gbase = s_group_base;
-    if (gbase == 0xffffffffu) return;
+    if (!s_slots_ok) return;
 
     // lanes whose window reaches beyond the expected table stay un-normalised (util.py:480-481)
     unsigned raw_lanes = 0;
@@ -317,14 +320,14 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     }
 
     // ---- phase 2: rows
-    unsigned g = gbase;
     unsigned rb = 0;                                  // parity of the min/max exchange buffer
     for (int xi = 0; xi < TX; xi++) {
         unsigned pm = passmask[xi];
         if (!pm) continue;
         const int x = x0 + xi;
-        if (tid == 0) { GroupHdr h; h.job = job; h.x = x; h.d0 = d0; h.mask = pm; hdr[g] = h; }
-        float *fdst = featT + (size_t)g * F * 32;
+        // dense packing: the k-th passing pixel of the row takes slot rowbase + k
+        const unsigned my_slot = s_rowbase[xi] + __popc(pm & ((1u << lane) - 1u));
+        float *fdst = featT + (size_t)(my_slot >> 5) * F * 32 + (my_slot & 31u);
 #pragma unroll 1
         for (int mode = 0; mode < 2; mode++) {
             unsigned mm = mode ? (pm & raw_lanes) : (pm & ~raw_lanes);
@@ -403,20 +406,17 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
                     const bool risky = !fast_ok || (dropped - 0x0ffffff8u <= 16u) || (f < 1.2e-38 && f != 0.0);
                     if (risky) f = __ddiv_rn(num, den);
                     f_nan |= (f != f);
-                    fdst[(size_t)(warp * S + b) * 32 + lane] = __double2float_rn(f);
+                    fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(f);
                 }
-            }
-            // windows with NaN features (constant window, or a zero in the expected table) take the
-            // general forest kernel, which implements sklearn's missing_go_to_left routing
-            {
-                unsigned nb = __ballot_sync(0xffffffffu, f_nan);
-                if (lane == 0 && nb) atomicOr(&nanmask[g], nb);
+                // windows with NaN features (constant window, or a zero in the expected table) take the
+                // general forest kernel, which implements sklearn's missing_go_to_left routing
+                if (f_nan) atomicOr(&nanmask[my_slot >> 5], 1u << (my_slot & 31u));
             }
         }
         if (warp == 0 && ((pm >> lane) & 1u)) {
-            if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)(g * 32u + lane);
+            pix[my_slot] = make_uint2((unsigned)job, ((unsigned)x << 16) | (unsigned)(d0 + lane));
+            if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)my_slot;
         }
-        g++;
     }
 }
 
@@ -438,14 +438,15 @@ struct ForestDev {
 
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
-k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict__ featT,
-         const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp)
+k_forest(ForestDev fr, const PixRef *__restrict__ pix, const float *__restrict__ featT,
+         const unsigned *__restrict__ slot_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp)
 {
     extern __shared__ float fs[];     // [WARPS][F][32]
     const int F = fr.n_features;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *my = fs + (size_t)warp * F * 32;
-    const unsigned ngroups = *group_counter;
+    const unsigned nslots = *slot_counter;
+    const unsigned ngroups = (nslots + 31u) >> 5;
     const int dlo = max(lower, W + 2);
     const int T = fr.n_trees;
     for (unsigned g = blockIdx.x * WARPS + warp; g < ngroups; g += gridDim.x * WARPS) {
@@ -453,8 +454,8 @@ k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict
         float4 *dst = reinterpret_cast<float4 *>(my);
         for (int k = lane; k < F * 8; k += 32) dst[k] = src[k];
         __syncwarp();
-        const GroupHdr h = hdr[g];
-        if ((h.mask >> lane) & 1u) {
+        const unsigned slot = g * 32u + lane;
+        if (slot < nslots) {
             double acc = 0.0;
             int t = 0;
             int base = fr.tree_off[0];
@@ -474,9 +475,9 @@ k_forest(ForestDev fr, const GroupHdr *__restrict__ hdr, const float *__restrict
                     node = left ? node + 1 : (int)(nd.y >> 9);
                 }
             }
-            double p = __ddiv_rn(acc, (double)T);
-            const JobDev J = jobs[h.job];
-            J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = p;
+            const PixRef px = pix[slot];
+            const JobDev J = jobs[px.x];
+            J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T);
         }
         __syncwarp();
     }
@@ -535,8 +536,8 @@ __device__ __forceinline__ int tree_of_node(const int *off, int ntree, int k)
 template <int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
-             const GroupHdr *__restrict__ hdr, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
-             const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
+             const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
+             const unsigned *__restrict__ slot_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
              double *__restrict__ accbuf, int first, int last)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -582,14 +583,14 @@ k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off,
     __syncthreads();
     for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = o_nodes + 8u * SM_U32(o_root + 4u * k);
     __syncthreads();
-    const unsigned ngroups = *group_counter;
+    const unsigned nslots = *slot_counter;
+    const unsigned ngroups = (nslots + 31u) >> 5;
     const int dlo = max(lower, W + 2);
     unsigned g = blockIdx.x;
     if (g < ngroups && tid == 0) {
         mbar_expect_tx(&mbar[0], tile_bytes);
         tma_load_1d(smem_raw, featT + (size_t)g * F * 32, tile_bytes, &mbar[0]);
     }
-    GroupHdr h = (g < ngroups) ? hdr[g] : GroupHdr{0, 0, 0, 0u};
     unsigned nanm = (g < ngroups) ? nanmask[g] : 0u;
     for (unsigned it = 0; g < ngroups; it++, g += gridDim.x) {
         const unsigned buf = it & 1u;
@@ -599,10 +600,9 @@ k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off,
             mbar_expect_tx(&mbar[buf ^ 1u], tile_bytes);
             tma_load_1d(smem_raw + (size_t)(buf ^ 1u) * tile_bytes, featT + (size_t)gn * F * 32, tile_bytes, &mbar[buf ^ 1u]);
         }
-        const GroupHdr hn = (gn < ngroups) ? hdr[gn] : GroupHdr{0, 0, 0, 0u};      // prefetch the next header
         const unsigned nanm_n = (gn < ngroups) ? nanmask[gn] : 0u;
         mbar_wait(&mbar[buf], (it >> 1) & 1u);
-        const bool active = ((h.mask & ~nanm) >> lane) & 1u;
+        const bool active = (g * 32u + lane < nslots) && !((nanm >> lane) & 1u);
         if (active) {
             const unsigned my = buf * tile_bytes + (unsigned)lane * 4u;
             const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
@@ -628,14 +628,14 @@ k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off,
                 double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
                 for (int tt = 0; tt < ntree; tt++) acc = __dadd_rn(acc, SM_F64(lv + 256u * (unsigned)tt));
                 if (last) {
-                    const JobDev J = jobs[h.job];
-                    J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
+                    const PixRef px = pix[g * 32u + lane];
+                    const JobDev J = jobs[px.x];
+                    J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T_total);
                 } else {
                     accbuf[(size_t)g * 32 + lane] = acc;
                 }
             }
         }
-        h = hn;
         nanm = nanm_n;
     }
 #undef SM_U2
@@ -659,8 +659,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 template <int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
-              const GroupHdr *__restrict__ hdr, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
-              const unsigned *__restrict__ group_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
+              const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
+              const unsigned *__restrict__ slot_counter, const JobDev *__restrict__ jobs, int lower, int W, int ndp,
               double *__restrict__ accbuf, int first, int last)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -704,7 +704,8 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
     __syncthreads();
     for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = o_nodes + 8u * SM_U32(o_root + 4u * k);
     __syncthreads();
-    const unsigned ngroups = *group_counter;
+    const unsigned nslots = *slot_counter;
+    const unsigned ngroups = (nslots + 31u) >> 5;
     const int dlo = max(lower, W + 2);
     const unsigned stride = gridDim.x;
     unsigned g = blockIdx.x;
@@ -718,16 +719,14 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
             tma_load_1d(smem_raw + tile_bytes, featT + (size_t)(g + stride) * F * 32, tile_bytes, &full[1]);
         }
     }
-    GroupHdr h = (g < ngroups) ? hdr[g] : GroupHdr{0, 0, 0, 0u};
     unsigned nanm = (g < ngroups) ? nanmask[g] : 0u;
     for (unsigned it = 0; g < ngroups; it++, g += stride) {
         const unsigned buf = it & 1u;
         const unsigned par = (it >> 1) & 1u;
         const unsigned gn = g + stride;
-        const GroupHdr hn = (gn < ngroups) ? hdr[gn] : GroupHdr{0, 0, 0, 0u};
         const unsigned nanm_n = (gn < ngroups) ? nanmask[gn] : 0u;
         mbar_wait(&full[buf], par);
-        const bool active = ((h.mask & ~nanm) >> lane) & 1u;
+        const bool active = (g * 32u + lane < nslots) && !((nanm >> lane) & 1u);
         if (active) {
             const unsigned my = buf * tile_bytes + (unsigned)lane * 4u;
             const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
@@ -753,8 +752,9 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
                 double acc = first ? 0.0 : accbuf[(size_t)g * 32 + lane];
                 for (int tt = 0; tt < ntree; tt++) acc = __dadd_rn(acc, SM_F64(lv + 256u * (unsigned)tt));
                 if (last) {
-                    const JobDev J = jobs[h.job];
-                    J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)T_total);
+                    const PixRef px = pix[g * 32u + lane];
+                    const JobDev J = jobs[px.x];
+                    J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T_total);
                 } else {
                     accbuf[(size_t)g * 32 + lane] = acc;
                 }
@@ -768,7 +768,6 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
                 tma_load_1d(smem_raw + (size_t)buf * tile_bytes, featT + (size_t)g2 * F * 32, tile_bytes, &full[buf]);
             }
         }
-        h = hn;
         nanm = nanm_n;
     }
 #undef SM_U2
@@ -778,19 +777,20 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
 }
 
 // pixels with NaN features: general traversal from global memory with missing_go_to_left routing
-__global__ void k_forest_nan(ForestDev fr, const GroupHdr *__restrict__ hdr, const unsigned *__restrict__ nanmask,
-                             const float *__restrict__ featT, const unsigned *__restrict__ group_counter,
+__global__ void k_forest_nan(ForestDev fr, const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask,
+                             const float *__restrict__ featT, const unsigned *__restrict__ slot_counter,
                              const JobDev *__restrict__ jobs, int lower, int W, int ndp)
 {
-    const unsigned ngroups = *group_counter;
+    const unsigned nslots = *slot_counter;
+    const unsigned ngroups = (nslots + 31u) >> 5;
     const int lane = threadIdx.x & 31;
     const int dlo = max(lower, W + 2);
     const int F = fr.n_features;
     for (unsigned g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * (blockDim.x >> 5)) {
         const unsigned nm = nanmask[g];
         if (!nm) continue;
-        const GroupHdr h = hdr[g];
-        if (!(((h.mask & nm) >> lane) & 1u)) continue;
+        const unsigned slot = g * 32u + lane;
+        if (!((nm >> lane) & 1u) || slot >= nslots) continue;
         const float *x = featT + (size_t)g * F * 32 + lane;
         double acc = 0.0;
         for (int t = 0; t < fr.n_trees; t++) {
@@ -805,8 +805,9 @@ __global__ void k_forest_nan(ForestDev fr, const GroupHdr *__restrict__ hdr, con
             }
             acc = __dadd_rn(acc, fr.leaf[base + node]);
         }
-        const JobDev J = jobs[h.job];
-        J.prob[(size_t)h.x * ndp + (h.d0 + lane - dlo)] = __ddiv_rn(acc, (double)fr.n_trees);
+        const PixRef px = pix[slot];
+        const JobDev J = jobs[px.x];
+        J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)fr.n_trees);
     }
 }
 
@@ -1098,7 +1099,7 @@ struct nlf_batch {
     JobDev *d_jobs = nullptr;
     int *d_tile_base = nullptr;
     int jobs_cap = 0;
-    GroupHdr *d_hdr = nullptr;
+    PixRef *d_pix = nullptr;
     float *d_featT = nullptr;
     unsigned *d_group_counter = nullptr;
     unsigned *d_nanmask = nullptr;
@@ -1430,7 +1431,7 @@ static int launch_features(nlf_batch *b, int total_tiles, int nexp)
     KLaunch k(c, P_FEATURE);
     k_features<W><<<total_tiles, FeatCfg<W>::NT, 0, c->stream>>>(
         b->d_jobs, b->d_tile_base, (int)b->jobs.size(), b->lower, b->upper, b->pitch, b->ndp, b->ndt, b->d_exp, nexp,
-        b->d_hdr, b->d_featT, b->d_group_counter, b->max_groups, b->d_overflow, b->d_nanmask);
+        b->d_pix, b->d_featT, b->d_group_counter, b->max_groups * 32u, b->d_overflow, b->d_nanmask);
     return NLF_OK;
 }
 
@@ -1484,7 +1485,7 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
         size_t smem = sizeof(float) * (size_t)GW * F * 32;
         NLF_CUDA(cudaFuncSetAttribute(k_forest<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KLaunch k(c, P_FOREST);
-        k_forest<GW><<<c->sm_count * 2, 32 * GW, smem, c->stream>>>(f->dev, b->d_hdr, b->d_featT, b->d_group_counter,
+        k_forest<GW><<<c->sm_count * 2, 32 * GW, smem, c->stream>>>(f->dev, b->d_pix, b->d_featT, b->d_group_counter,
                                                                     b->d_jobs, b->lower, w, b->ndp);
         NLF_CUDA(cudaGetLastError());
         return NLF_OK;
@@ -1511,7 +1512,7 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
             NLF_CUDA(cudaFuncSetAttribute(KERN<A>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                           (int)(smem_max - 64)));                                                   \
             KERN<A><<<c->sm_count, 32 * A, smem, c->stream>>>(                                                      \
-                f->d_nodes2, f->d_off, t0, t1, T, F, b->d_hdr, b->d_nanmask, b->d_featT, b->d_group_counter,        \
+                f->d_nodes2, f->d_off, t0, t1, T, F, b->d_pix, b->d_nanmask, b->d_featT, b->d_group_counter,        \
                 b->d_jobs, b->lower, w, b->ndp, acc, p == 0, p == nparts - 1);                                      \
         } while (0)
         switch (cfg) {
@@ -1526,7 +1527,7 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
     {
         // pixels with NaN features (rare: constant windows) through the general kernel
         KLaunch k(c, P_FOREST);
-        k_forest_nan<<<c->sm_count * 4, 256, 0, c->stream>>>(f->dev, b->d_hdr, b->d_nanmask, b->d_featT,
+        k_forest_nan<<<c->sm_count * 4, 256, 0, c->stream>>>(f->dev, b->d_pix, b->d_nanmask, b->d_featT,
                                                              b->d_group_counter, b->d_jobs, b->lower, w, b->ndp);
         NLF_CUDA(cudaGetLastError());
     }
@@ -1663,7 +1664,7 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     const int tiles = b->total_tiles;
     if (groups > 0xfffffff0LL) return fail(NLF_ERR_ARG, "batch too large: %lld feature groups; split the batch", groups);
     b->max_groups = (unsigned)groups;
-    NLF_CUDA(cudaMallocAsync(&b->d_hdr, sizeof(GroupHdr) * (size_t)groups, c->stream));
+    NLF_CUDA(cudaMallocAsync(&b->d_pix, sizeof(PixRef) * (size_t)groups * 32, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_featT, sizeof(float) * (size_t)groups * F * 32, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned), c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
@@ -1953,7 +1954,7 @@ static void free_score_outputs(nlf_batch *b)
     auto fr = [&](auto *&p) { if (p) { cudaFreeAsync(p, s); p = nullptr; } };
     fr(b->d_prob); fr(b->d_slot);
     fr(b->d_don_job); fr(b->d_don_i); fr(b->d_don_j); fr(b->d_don_p); fr(b->d_don_v);
-    fr(b->d_hdr); fr(b->d_featT); fr(b->d_group_counter); fr(b->d_nanmask); fr(b->d_overflow); fr(b->d_exp);
+    fr(b->d_pix); fr(b->d_featT); fr(b->d_group_counter); fr(b->d_nanmask); fr(b->d_overflow); fr(b->d_exp);
 }
 
 // Forget the results of a scored batch but keep the matrices resident in HBM, so that the
