@@ -339,7 +339,6 @@ def main():
         t_dbg = time.perf_counter()
         loops_e, counts_e = step_e2e()
         if os.environ.get("NLF_BENCH_DEBUG"):
-            ctx.sync()
             print("e2e step %.2f ms" % (1e3 * (time.perf_counter() - t_dbg)), file=sys.stderr)
     ms_e = ctx.timer_stop()
     wall_e = 1000.0 * (time.perf_counter() - t_e2e)

@@ -52,6 +52,48 @@ struct nlf_ctx {
     long long prof_n[nlf::P_NCLASS] = {0};
     int sm_count = 148;
 
+    // Grow-only cache of large device buffers (>= 1 MB).  Every operation of a context is ordered on
+    // its single stream, so a buffer handed back here can be reused by the next request at once;
+    // steady-state steps then make no driver allocation at all (cudaMalloc of multi-GB feature
+    // buffers costs tens of ms to seconds and showed up as latency spikes in the end-to-end path).
+    struct Big { void *p; size_t bytes; bool busy; };
+    std::vector<Big> bigs;
+    cudaError_t big_alloc(void **out, size_t bytes)
+    {
+        int best = -1;
+        for (int i = 0; i < (int)bigs.size(); i++)
+            if (!bigs[i].busy && bigs[i].bytes >= bytes && bigs[i].bytes <= bytes + bytes / 4 + (1 << 20) &&
+                (best < 0 || bigs[i].bytes < bigs[best].bytes))
+                best = i;
+        if (best >= 0) { bigs[best].busy = true; *out = bigs[best].p; return cudaSuccess; }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            // release idle cached buffers and retry once
+            cudaGetLastError();
+            cudaStreamSynchronize(stream);
+            for (auto &b : bigs) if (!b.busy && b.p) { cudaFree(b.p); b.p = nullptr; }
+            std::vector<Big> keep;
+            for (auto &b : bigs) if (b.p) keep.push_back(b);
+            bigs.swap(keep);
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) return e;
+        }
+        bigs.push_back({p, bytes, true});
+        *out = p;
+        return cudaSuccess;
+    }
+    void big_free(void *p)
+    {
+        if (!p) return;
+        for (auto &b : bigs) if (b.p == p) { b.busy = false; return; }
+    }
+    void big_release_all()
+    {
+        for (auto &b : bigs) if (b.p) cudaFree(b.p);
+        bigs.clear();
+    }
+
     cudaEvent_t get_event()
     {
         if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }

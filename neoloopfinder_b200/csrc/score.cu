@@ -1075,6 +1075,7 @@ constexpr int NLF_MAX_JOBS = 16384;     // jobs per batch (status / counter pool
 struct HostJob {
     int n = 0;
     double *d_band = nullptr;
+    bool band_big = true;       // from the context's big-buffer cache (false: cudaMallocAsync, assembly export)
     size_t prob_off = 0;         // offset (cells) of this job inside the batch's prob / slot pools
     unsigned long long counts[4] = {0, 0, 0, 0};
     int status = 0;
@@ -1162,6 +1163,7 @@ NLF_EXPORT int nlf_ctx_destroy(nlf_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->prof_resolve();
+    c->big_release_all();
     for (auto e : c->free_events) cudaEventDestroy(e);
     cudaEventDestroy(c->t0);
     cudaEventDestroy(c->t1);
@@ -1369,8 +1371,8 @@ NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
     HostJob j;
     j.n = n;
     double *d_dense;
-    NLF_CUDA(cudaMallocAsync(&d_dense, sizeof(double) * (size_t)n * n, c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_band, sizeof(double) * (size_t)n * b->pitch, c->stream));
+    NLF_CUDA(c->big_alloc((void **)&d_dense, sizeof(double) * (size_t)n * n));
+    NLF_CUDA(c->big_alloc((void **)&j.d_band, sizeof(double) * (size_t)n * b->pitch));
     NLF_CUDA(cudaMemcpyAsync(d_dense, G, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
     {
         KLaunch k(c, P_BANDIFY);
@@ -1378,7 +1380,7 @@ NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
         k_bandify<<<grid, 128, 0, c->stream>>>(d_dense, n, b->bw, b->pitch, j.d_band, b->d_status + b->jobs.size());
     }
     NLF_CUDA(cudaGetLastError());
-    NLF_CUDA(cudaFreeAsync(d_dense, c->stream));
+    c->big_free(d_dense);
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
 }
@@ -1394,8 +1396,8 @@ NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int p
     HostJob j;
     j.n = n;
     double *d_src;
-    NLF_CUDA(cudaMallocAsync(&d_src, sizeof(double) * (size_t)n * pitch, c->stream));
-    NLF_CUDA(cudaMallocAsync(&j.d_band, sizeof(double) * (size_t)n * b->pitch, c->stream));
+    NLF_CUDA(c->big_alloc((void **)&d_src, sizeof(double) * (size_t)n * pitch));
+    NLF_CUDA(c->big_alloc((void **)&j.d_band, sizeof(double) * (size_t)n * b->pitch));
     NLF_CUDA(cudaMemcpyAsync(d_src, band, sizeof(double) * (size_t)n * pitch, cudaMemcpyHostToDevice, c->stream));
     {
         KLaunch k(c, P_BANDIFY);
@@ -1403,7 +1405,7 @@ NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int p
         k_band_copy<<<grid, 128, 0, c->stream>>>(d_src, n, pitch, b->bw, b->pitch, j.d_band);
     }
     NLF_CUDA(cudaGetLastError());
-    NLF_CUDA(cudaFreeAsync(d_src, c->stream));
+    c->big_free(d_src);
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
 }
@@ -1418,6 +1420,7 @@ NLF_EXPORT int nlf_batch_add_assembly(nlf_batch *b, nlf_assembly *a)
     HostJob j;
     rc = nlf_assembly_export_band(a, b->bw, b->pitch, &j.d_band, &j.n);
     if (rc) return rc;
+    j.band_big = false;
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
 }
@@ -1650,8 +1653,8 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
         cells += (size_t)j.n * b->ndp;
         band_cells += (long long)j.n * (b->upper - dlo + 1);
     }
-    NLF_CUDA(cudaMallocAsync(&b->d_prob, sizeof(double) * cells, c->stream));
-    if (b->keep_slots) NLF_CUDA(cudaMallocAsync(&b->d_slot, sizeof(int) * cells, c->stream));
+    NLF_CUDA(c->big_alloc((void **)&b->d_prob, sizeof(double) * cells));
+    if (b->keep_slots) NLF_CUDA(c->big_alloc((void **)&b->d_slot, sizeof(int) * cells));
     b->don_cap = std::max(1LL, std::min(band_cells, 1LL << 23));
     NLF_CUDA(cudaMallocAsync(&b->d_don_job, sizeof(int) * b->don_cap, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_don_i, sizeof(int) * b->don_cap, c->stream));
@@ -1664,10 +1667,10 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     const int tiles = b->total_tiles;
     if (groups > 0xfffffff0LL) return fail(NLF_ERR_ARG, "batch too large: %lld feature groups; split the batch", groups);
     b->max_groups = (unsigned)groups;
-    NLF_CUDA(cudaMallocAsync(&b->d_pix, sizeof(PixRef) * (size_t)groups * 32, c->stream));
-    NLF_CUDA(cudaMallocAsync(&b->d_featT, sizeof(float) * (size_t)groups * F * 32, c->stream));
+    NLF_CUDA(c->big_alloc((void **)&b->d_pix, sizeof(PixRef) * (size_t)groups * 32));
+    NLF_CUDA(c->big_alloc((void **)&b->d_featT, sizeof(float) * (size_t)groups * F * 32));
     NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned), c->stream));
-    NLF_CUDA(cudaMallocAsync(&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
+    NLF_CUDA(c->big_alloc((void **)&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1)));
     NLF_CUDA(cudaMemsetAsync(b->d_nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_overflow, sizeof(int), c->stream));
     NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
@@ -1952,9 +1955,10 @@ static void free_score_outputs(nlf_batch *b)
 {
     cudaStream_t s = b->ctx->stream;
     auto fr = [&](auto *&p) { if (p) { cudaFreeAsync(p, s); p = nullptr; } };
-    fr(b->d_prob); fr(b->d_slot);
+    auto frb = [&](auto *&p) { if (p) { b->ctx->big_free(p); p = nullptr; } };
+    frb(b->d_prob); frb(b->d_slot); frb(b->d_pix); frb(b->d_featT); frb(b->d_nanmask);
     fr(b->d_don_job); fr(b->d_don_i); fr(b->d_don_j); fr(b->d_don_p); fr(b->d_don_v);
-    fr(b->d_pix); fr(b->d_featT); fr(b->d_group_counter); fr(b->d_nanmask); fr(b->d_overflow); fr(b->d_exp);
+    fr(b->d_group_counter); fr(b->d_overflow); fr(b->d_exp);
 }
 
 // Forget the results of a scored batch but keep the matrices resident in HBM, so that the
@@ -2046,7 +2050,9 @@ NLF_EXPORT int nlf_batch_destroy(nlf_batch *b)
     cudaStream_t s = c->stream;
     free_score_outputs(b);
     for (auto &j : b->jobs)
-        if (j.d_band) cudaFreeAsync(j.d_band, s);
+        if (j.d_band) {
+            if (j.band_big) c->big_free(j.d_band); else cudaFreeAsync(j.d_band, s);
+        }
     if (b->d_status) cudaFreeAsync(b->d_status, s);
     if (b->d_counts) cudaFreeAsync(b->d_counts, s);
     if (b->d_scratch) cudaFreeAsync(b->d_scratch, s);
