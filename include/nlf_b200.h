@@ -118,6 +118,10 @@ int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expected, int nex
 int nlf_batch_counts(nlf_batch *b, long long *n_cand, long long *n_scored, long long *n_donuts);
 /* Donuts of one job: coordinates, probability, and the contact value M[i,j]. */
 int nlf_batch_fetch_donuts(nlf_batch *b, int job, int *i, int *j, double *prob, double *value);
+/* Donuts of ALL jobs in one call (arrays of capacity cap; any order; job[k] tags the owner).
+ * Pass job = NULL to query *n_total only. */
+int nlf_batch_fetch_donuts_all(nlf_batch *b, long long cap, int *job, int *i, int *j, double *prob,
+                               double *value, long long *n_total);
 /* Every scored pixel of one job in candidate order (diagonal-major, row-ascending):
  * clist and probas of Peakachu.predict.  cap = capacity of the arrays. */
 int nlf_batch_fetch_scored(nlf_batch *b, int job, long long cap, int *i, int *j, double *prob);

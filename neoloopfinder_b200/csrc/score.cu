@@ -178,6 +178,42 @@ __global__ void k_isotonic(const JobDev *__restrict__ jobs, int lower, int upper
     }
 }
 
+// shared-memory / mbarrier / TMA helpers (split-phase barriers in k_features, TMA pipeline in the forest kernels)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    const unsigned addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
 // =============================================================================================
 // K7 feature kernel.
 // Block = S warps (S = 2W+1); tile = TX matrix rows x 32 consecutive diagonals.  Warp a owns
@@ -224,6 +260,9 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     __shared__ unsigned passmask[TX];
     __shared__ unsigned s_rowbase[TX];       // first feature slot of every tile row
     __shared__ unsigned s_slots_ok;
+    __shared__ unsigned char s_items[2 * TX];
+    __shared__ int s_nitems;
+    __shared__ __align__(8) unsigned long long s_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- tile -> (job, x0, d0)
@@ -319,103 +358,119 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
         raw_lanes = __ballot_sync(0xffffffffu, raw);
     }
 
-    // ---- phase 2: rows
-    unsigned rb = 0;                                  // parity of the min/max exchange buffer
-    for (int xi = 0; xi < TX; xi++) {
-        unsigned pm = passmask[xi];
-        if (!pm) continue;
+    // ---- phase 2: rows.  Work items = (tile row, O/E or raw source) that have at least one window.
+    // Per item: axis-1 pass -> row min/max to shared memory -> mbarrier ARRIVE -> axis-0 pass of the
+    // NEXT item (independent work that hides the barrier latency) -> mbarrier WAIT -> normalise, store.
+    if (tid == 0) {
+        int k = 0;
+        for (int xi = 0; xi < TX; xi++) {
+            unsigned pm = passmask[xi];
+            if (pm & ~raw_lanes) s_items[k++] = (unsigned char)(xi * 2);
+            if (pm & raw_lanes) s_items[k++] = (unsigned char)(xi * 2 + 1);
+        }
+        s_nitems = k;
+        mbar_init(&s_bar[0], NT);
+        mbar_init(&s_bar[1], NT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nitems = s_nitems;
+    auto stage_a = [&](int item) {
+        // axis-0 pass, warp a -> Vx[a][*]  (row a is produced and consumed by warp a only)
+        const int xi = item >> 1;
+        const double (*T)[TC] = (item & 1) ? Rt : Et;
+        const int a = warp;
+        int ra[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) ra[k] = reflect_idx(a + k - 4, S);
+        for (int cc = lane; cc < VC; cc += 32) {
+            // src(a', cc) = T[xi + a'][cc - a' + 2W]
+            double v = __dmul_rn(T[xi + ra[4]][cc - ra[4] + 2 * W], c_gw[4]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double l = T[xi + ra[j]][cc - ra[j] + 2 * W];
+                double r = T[xi + ra[8 - j]][cc - ra[8 - j] + 2 * W];
+                v = __dadd_rn(v, __dmul_rn(__dadd_rn(l, r), c_gw[j]));
+            }
+            Vx[a][cc] = v;
+        }
+        __syncwarp();
+    };
+    if (nitems > 0) stage_a(s_items[0]);
+    for (int it = 0; it < nitems; it++) {
+        const int item = s_items[it];
+        const int xi = item >> 1;
+        const unsigned pm = passmask[xi];
+        const unsigned mm = (item & 1) ? (pm & raw_lanes) : (pm & ~raw_lanes);
         const int x = x0 + xi;
+        const unsigned rb = it & 1u;
         // dense packing: the k-th passing pixel of the row takes slot rowbase + k
         const unsigned my_slot = s_rowbase[xi] + __popc(pm & ((1u << lane) - 1u));
         float *fdst = featT + (size_t)(my_slot >> 5) * F * 32 + (my_slot & 31u);
-#pragma unroll 1
-        for (int mode = 0; mode < 2; mode++) {
-            unsigned mm = mode ? (pm & raw_lanes) : (pm & ~raw_lanes);
-            if (!mm) continue;
-            const double (*T)[TC] = mode ? Rt : Et;
-            // stage A: axis-0 pass, warp a -> Vx[a][*]  (row a is produced and consumed by warp a only)
-            {
-                const int a = warp;
-                int ra[9];
+        // stage B: axis-1 pass for window row a = warp, window of lane
+        double in[S], out[S];
 #pragma unroll
-                for (int k = 0; k < 9; k++) ra[k] = reflect_idx(a + k - 4, S);
-                for (int cc = lane; cc < VC; cc += 32) {
-                    // src(a', cc) = T[xi + a'][cc - a' + 2W]
-                    double v = __dmul_rn(T[xi + ra[4]][cc - ra[4] + 2 * W], c_gw[4]);
+        for (int b = 0; b < S; b++) in[b] = Vx[warp][lane + b];
+        __syncwarp();                                  // Vx[warp] may now be overwritten (next stage A)
+        double rmin, rmax;
+        bool has_nan = false;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        double l = T[xi + ra[j]][cc - ra[j] + 2 * W];
-                        double r = T[xi + ra[8 - j]][cc - ra[8 - j] + 2 * W];
-                        v = __dadd_rn(v, __dmul_rn(__dadd_rn(l, r), c_gw[j]));
-                    }
-                    Vx[a][cc] = v;
-                }
+        for (int b = 0; b < S; b++) {
+            double v = __dmul_rn(in[b], c_gw[4]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // pair (b-4+j, b+4-j), outermost first
+                const int il = (b - 4 + j) < 0 ? -(b - 4 + j) - 1 : (b - 4 + j);
+                const int ir = (b + 4 - j) >= S ? 2 * S - 1 - (b + 4 - j) : (b + 4 - j);
+                v = __dadd_rn(v, __dmul_rn(__dadd_rn(in[il], in[ir]), c_gw[j]));
             }
-            __syncwarp();
-            // stage B: axis-1 pass for window row a = warp, window of lane
-            double in[S], out[S];
+            out[b] = v;
+            has_nan |= (v != v);
+            if (b == 0) { rmin = v; rmax = v; }
+            else { rmin = (v < rmin) ? v : rmin; rmax = (v > rmax) ? v : rmax; }
+        }
+        if (has_nan) { rmin = qnan; rmax = qnan; }
+        red_min[rb][warp][lane] = rmin;
+        red_max[rb][warp][lane] = rmax;
+        mbar_arrive(&s_bar[rb]);                       // release: my row's min/max are published
+        if (it + 1 < nitems) stage_a(s_items[it + 1]);
+        mbar_wait(&s_bar[rb], (it >> 1) & 1u);         // acquire: all window rows are in
+        double mn = red_min[rb][0][lane], mx = red_max[rb][0][lane];
+        bool nn = (mn != mn);
 #pragma unroll
-            for (int b = 0; b < S; b++) in[b] = Vx[warp][lane + b];
-            __syncwarp();                              // Vx[warp] may be overwritten by the next stage A
-            double rmin, rmax;
-            bool has_nan = false;
+        for (int a = 1; a < S; a++) {
+            double u = red_min[rb][a][lane], v = red_max[rb][a][lane];
+            nn |= (u != u);
+            mn = (u < mn) ? u : mn;
+            mx = (v > mx) ? v : mx;
+        }
+        if (nn) { mn = qnan; mx = qnan; }
+        if ((mm >> lane) & 1u) {
+            bool f_nan = false;
+            const double den = __dsub_rn(mx, mn);
+            // float32(fl64(num/den)) without 13 fp64 divisions: p = fl64(num * fl64(1/den)) is within
+            // 2.01 ulp64 of the exact quotient, so it rounds to the same float32 unless it sits within
+            // 8 ulp64 of a float32 rounding boundary (low 29 mantissa bits ~ 0x10000000) or in the
+            // float32 subnormal range; those (about 1 in 3e7) take the exact division.
+            const bool fast_ok = (den > 1e-290) && (den < 1e300);
+            const double rden = __ddiv_rn(1.0, fast_ok ? den : 1.0);
 #pragma unroll
             for (int b = 0; b < S; b++) {
-                double v = __dmul_rn(in[b], c_gw[4]);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    // pair (b-4+j, b+4-j), outermost first
-                    const int il = (b - 4 + j) < 0 ? -(b - 4 + j) - 1 : (b - 4 + j);
-                    const int ir = (b + 4 - j) >= S ? 2 * S - 1 - (b + 4 - j) : (b + 4 - j);
-                    v = __dadd_rn(v, __dmul_rn(__dadd_rn(in[il], in[ir]), c_gw[j]));
-                }
-                out[b] = v;
-                has_nan |= (v != v);
-                if (b == 0) { rmin = v; rmax = v; }
-                else { rmin = (v < rmin) ? v : rmin; rmax = (v > rmax) ? v : rmax; }
+                const double num = __dsub_rn(out[b], mn);
+                double f = __dmul_rn(num, rden);
+                const unsigned dropped = (unsigned)__double2loint(f) & 0x1fffffffu;
+                const bool risky = !fast_ok || (dropped - 0x0ffffff8u <= 16u) || (f < 1.2e-38 && f != 0.0);
+                if (risky) f = __ddiv_rn(num, den);
+                f_nan |= (f != f);
+                fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(f);
             }
-            if (has_nan) { rmin = qnan; rmax = qnan; }
-            red_min[rb][warp][lane] = rmin;
-            red_max[rb][warp][lane] = rmax;
-            __syncthreads();
-            double mn = red_min[rb][0][lane], mx = red_max[rb][0][lane];
-            bool nn = (mn != mn);
-#pragma unroll
-            for (int a = 1; a < S; a++) {
-                double u = red_min[rb][a][lane], v = red_max[rb][a][lane];
-                nn |= (u != u);
-                mn = (u < mn) ? u : mn;
-                mx = (v > mx) ? v : mx;
+            // windows with NaN features (constant window, or a zero in the expected table) take the
+            // general forest kernel, which implements sklearn's missing_go_to_left routing
+            if (f_nan) atomicOr(&nanmask[my_slot >> 5], 1u << (my_slot & 31u));
+            if (warp == 0) {
+                pix[my_slot] = make_uint2((unsigned)job, ((unsigned)x << 16) | (unsigned)(d0 + lane));
+                if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)my_slot;
             }
-            rb ^= 1u;            // the buffer is reused two barriers from now: every warp has read it by then
-            if (nn) { mn = qnan; mx = qnan; }
-            bool f_nan = false;
-            if ((mm >> lane) & 1u) {
-                const double den = __dsub_rn(mx, mn);
-                // float32(fl64(num/den)) without 13 fp64 divisions: p = fl64(num * fl64(1/den)) is within
-                // 2.01 ulp64 of the exact quotient, so it rounds to the same float32 unless it sits within
-                // 8 ulp64 of a float32 rounding boundary (low 29 mantissa bits ~ 0x10000000) or in the
-                // float32 subnormal range; those (about 1 in 3e7) take the exact division.
-                const bool fast_ok = (den > 1e-290) && (den < 1e300);
-                const double rden = __ddiv_rn(1.0, fast_ok ? den : 1.0);
-#pragma unroll
-                for (int b = 0; b < S; b++) {
-                    const double num = __dsub_rn(out[b], mn);
-                    double f = __dmul_rn(num, rden);
-                    const unsigned dropped = (unsigned)__double2loint(f) & 0x1fffffffu;
-                    const bool risky = !fast_ok || (dropped - 0x0ffffff8u <= 16u) || (f < 1.2e-38 && f != 0.0);
-                    if (risky) f = __ddiv_rn(num, den);
-                    f_nan |= (f != f);
-                    fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(f);
-                }
-                // windows with NaN features (constant window, or a zero in the expected table) take the
-                // general forest kernel, which implements sklearn's missing_go_to_left routing
-                if (f_nan) atomicOr(&nanmask[my_slot >> 5], 1u << (my_slot & 31u));
-            }
-        }
-        if (warp == 0 && ((pm >> lane) & 1u)) {
-            pix[my_slot] = make_uint2((unsigned)job, ((unsigned)x << 16) | (unsigned)(d0 + lane));
-            if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)my_slot;
         }
     }
 }
@@ -481,36 +536,6 @@ k_forest(ForestDev fr, const PixRef *__restrict__ pix, const float *__restrict__
         }
         __syncwarp();
     }
-}
-
-// shared-memory / mbarrier / TMA helpers for the cooperative forest kernels
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned done = 0;
-    const unsigned addr = smem_u32(bar);
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // tree (0..ntree-1) that owns part-local node k; off[] = part-local tree offsets, off[ntree] = part_nodes
@@ -651,11 +676,6 @@ k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off,
 // next tile at once; the tile's summing warp (round robin) waits for `done`, adds the leaf values
 // in tree order, resets the tree counters and only then issues the TMA copy that refills the
 // buffer two tiles later -- which is also what protects leafv/cnt from early reuse.
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
@@ -1788,6 +1808,30 @@ NLF_EXPORT int nlf_batch_fetch_donuts(nlf_batch *b, int job, int *i, int *j, dou
         prob[k] = b->h_don_p[idx[k]];
         value[k] = b->h_don_v[idx[k]];
     }
+    return NLF_OK;
+}
+
+// The whole Donut list of the batch at once (arrays of n_total entries, any order): job, i, j, p, v.
+NLF_EXPORT int nlf_batch_fetch_donuts_all(nlf_batch *b, long long cap, int *job, int *i, int *j, double *prob,
+                                          double *value, long long *n_total)
+{
+    if (!b || !n_total) return fail(NLF_ERR_ARG, "nlf_batch_fetch_donuts_all: NULL argument");
+    if (!b->scored) return fail(NLF_ERR_STATE, "batch not scored yet");
+    int rc = batch_sync_counts(b);
+    if (rc) return rc;
+    if ((long long)b->n_donuts_total > b->don_cap) return fail(NLF_ERR_ARG, "Donut capacity exceeded");
+    *n_total = (long long)b->n_donuts_total;
+    if (!job) return NLF_OK;                         // size query
+    if (cap < (long long)b->n_donuts_total) return fail(NLF_ERR_ARG, "capacity %lld < %llu Donuts", cap, b->n_donuts_total);
+    const size_t m = (size_t)b->n_donuts_total;
+    if (m == 0) return NLF_OK;
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaMemcpyAsync(job, b->d_don_job, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(i, b->d_don_i, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(j, b->d_don_j, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(prob, b->d_don_p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaMemcpyAsync(value, b->d_don_v, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
     return NLF_OK;
 }
 

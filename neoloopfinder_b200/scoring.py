@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, f64, i32, ptr
 
-__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "pool_buckets", "local_clustering_gpu",
+__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "pool_buckets", "pool_flat", "local_clustering_gpu",
            "score_and_pool", "score_matrices"]
 
 
@@ -172,6 +172,19 @@ class ScoreBatch:
                                                      ptr(p, C.c_double), ptr(v, C.c_double)))
         return i, j, p, v
 
+    def donuts_all(self):
+        """(job, i, j, prob, value) arrays of every Donut of the batch: one device-to-host copy."""
+        n = C.c_longlong(0)
+        L = _lib.load()
+        check(L.nlf_batch_fetch_donuts_all(self.h, 0, None, None, None, None, None, C.byref(n)))
+        m = n.value
+        job = np.empty(m, np.int32); i = np.empty(m, np.int32); j = np.empty(m, np.int32)
+        p = np.empty(m, np.float64); v = np.empty(m, np.float64)
+        if m:
+            check(L.nlf_batch_fetch_donuts_all(self.h, m, ptr(job, C.c_int), ptr(i, C.c_int), ptr(j, C.c_int),
+                                               ptr(p, C.c_double), ptr(v, C.c_double), C.byref(n)))
+        return job, i, j, p, v
+
     def scored(self, job: int):
         m = int(self.counts()[1][job])
         i = np.empty(m, np.int32); j = np.empty(m, np.int32); p = np.empty(m, np.float64)
@@ -219,9 +232,9 @@ class ScoreBatch:
             pass
 
 
-def pool_buckets(buckets: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]], res: int, min_count: int = 2,
-                 r: int = 15000, ctx=None) -> List[np.ndarray]:
-    """Peakachu._local_clustering for a list of buckets [(i, j, value)] -> list of keep masks.
+def pool_flat(off, pi, pj, val, res: int, min_count: int = 2, r: int = 15000, ctx=None) -> np.ndarray:
+    """Peakachu._local_clustering for buckets given as one concatenated point list
+    (points of bucket k = [off[k], off[k+1])) -> keep mask over the points.
 
     Below 10 kb scipy's peak-distance filter can remove peaks, and among EQUAL peak heights its
     outcome follows numpy.argsort's implementation-defined tie order.  The kernel reports when
@@ -231,18 +244,12 @@ def pool_buckets(buckets: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]], r
     """
     ctx = ctx or _lib.Context.get()
     L = _lib.load()
-    nb = len(buckets)
-    if nb == 0:
-        return []
-    sizes = [len(b[0]) for b in buckets]
-    off = np.zeros(nb + 1, dtype=np.int64)
-    off[1:] = np.cumsum(sizes)
-    total = int(off[-1])
-    if total == 0:
-        return [np.zeros(0, dtype=bool) for _ in buckets]
-    pi = i32(np.concatenate([np.asarray(b[0]) for b in buckets]))
-    pj = i32(np.concatenate([np.asarray(b[1]) for b in buckets]))
-    val = f64(np.concatenate([np.asarray(b[2]) for b in buckets]))
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    nb = len(off) - 1
+    total = int(off[-1]) if nb > 0 else 0
+    if nb <= 0 or total == 0:
+        return np.zeros(total, dtype=bool)
+    pi, pj, val = i32(pi), i32(pj), f64(val)
     xo = yo = None
     xo_off = yo_off = None
     if max(r // res, 2) > 2:
@@ -269,7 +276,25 @@ def pool_buckets(buckets: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]], r
                      None if xo is None else ptr(xo, C.c_int), None if xo is None else ptr(xo_off, C.c_int64),
                      None if yo is None else ptr(yo, C.c_int), None if yo is None else ptr(yo_off, C.c_int64),
                      ptr(keep, C.c_ubyte)))
-    return [keep[off[k]:off[k + 1]].astype(bool) for k in range(nb)]
+    return keep.astype(bool)
+
+
+def pool_buckets(buckets: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]], res: int, min_count: int = 2,
+                 r: int = 15000, ctx=None) -> List[np.ndarray]:
+    """Peakachu._local_clustering for a list of buckets [(i, j, value)] -> list of keep masks."""
+    nb = len(buckets)
+    if nb == 0:
+        return []
+    sizes = [len(b[0]) for b in buckets]
+    off = np.zeros(nb + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    if int(off[-1]) == 0:
+        return [np.zeros(0, dtype=bool) for _ in buckets]
+    pi = np.concatenate([np.asarray(b[0]) for b in buckets])
+    pj = np.concatenate([np.asarray(b[1]) for b in buckets])
+    val = np.concatenate([np.asarray(b[2]) for b in buckets])
+    keep = pool_flat(off, pi, pj, val, res, min_count, r, ctx)
+    return [keep[off[k]:off[k + 1]] for k in range(nb)]
 
 
 def local_clustering_gpu(ij, val, res, min_count=2, r=15000, chain_i=None, chain_j=None, ctx=None):
@@ -304,44 +329,49 @@ def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, mi
     """
     batch.score(forest, exp_arr, thre, forest.w)
     n_cand, n_scored, n_don = batch.counts()
-    donuts = []
-    buckets, owners = [], []
-    for job in range(batch.njobs):
-        if n_scored[job] < 2:                      # callers.py:619-620
-            donuts.append(None)
-            continue
-        di, dj, dp, dv = batch.donuts(job)
-        donuts.append((di, dj, dp, dv))
-        if no_pool or len(di) == 0:
-            continue
-        ch = None if chains is None else chains[job]
-        if ch is None:
-            key = np.zeros(len(di), dtype=np.int64)
-        else:
-            ch = np.asarray(ch)
-            key = ch[di].astype(np.int64) * (1 << 24) + ch[dj]
-        for kk in np.unique(key):
-            sel = np.where(key == kk)[0]
-            buckets.append((di[sel], dj[sel], dv[sel]))
-            owners.append((job, sel))
-    masks = pool_buckets(buckets, res, min_count, r, batch.ctx) if buckets else []
-    keep = {}
-    for (job, sel), m in zip(owners, masks):
-        keep.setdefault(job, []).append(sel[m])
-    loops = []
+    dj_, di, dj, dp, dv = batch.donuts_all()
+    nj = batch.njobs
     empty = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64))
-    for job in range(batch.njobs):
-        d = donuts[job]
-        if d is None:
-            loops.append(empty)
-            continue
-        di, dj, dp, dv = d
-        if no_pool:
-            sel = np.arange(len(di))
-        else:
-            parts = keep.get(job, [])
-            sel = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
-        loops.append((di[sel], dj[sel], dp[sel]))
+    # callers.py:619-620: fewer than two scored windows -> no call at all for that matrix
+    if len(dj_):
+        ok = n_scored[dj_] >= 2
+        if not ok.all():
+            dj_, di, dj, dp, dv = dj_[ok], di[ok], dj[ok], dp[ok], dv[ok]
+    if len(dj_) == 0:
+        return [empty] * nj, (n_cand, n_scored, n_don)
+    if no_pool:
+        keep = np.ones(len(dj_), dtype=bool)
+        order = np.argsort(dj_, kind="stable")
+    else:
+        # bucket key = (job, chain of i, chain of j)   (callers.py:671-683)
+        ci = np.zeros(len(dj_), dtype=np.int64)
+        cj = np.zeros(len(dj_), dtype=np.int64)
+        if chains is not None:
+            for job in np.unique(dj_):
+                ch = chains[job]
+                if ch is None:
+                    continue
+                sel = dj_ == job
+                ch = np.asarray(ch)
+                ci[sel] = ch[di[sel]]
+                cj[sel] = ch[dj[sel]]
+        key = (dj_.astype(np.int64) << 40) | (ci << 20) | cj
+        order = np.argsort(key, kind="stable")
+        ks = key[order]
+        starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+        off = np.r_[starts, len(ks)].astype(np.int64)
+        keep_sorted = pool_flat(off, di[order], dj[order], dv[order], res, min_count, r, batch.ctx)
+        keep = np.empty(len(dj_), dtype=bool)
+        keep[order] = keep_sorted
+    loops = [empty] * nj
+    sel = order[keep[order]]
+    js = dj_[sel]
+    if len(sel):
+        cuts = np.flatnonzero(np.r_[True, js[1:] != js[:-1]])
+        ends = np.r_[cuts[1:], len(sel)]
+        for a, e in zip(cuts, ends):
+            idx = sel[a:e]
+            loops[int(js[a])] = (di[idx], dj[idx], dp[idx])
     return loops, (n_cand, n_scored, n_don)
 
 

@@ -115,3 +115,88 @@ def test_tiny_matrix_raises_like_reference():
     from neoloopfinder_b200.callers import Peakachu
     with pytest.raises(ValueError):
         Peakachu(np.triu(np.ones((8, 8))), upper=4000000, res=10000)
+
+
+def test_band_input_equals_dense_input():
+    """the banded (n x 414) input form behind the same scoring path."""
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.forest import load_forest
+    from neoloopfinder_b200.scoring import ScoreBatch
+    from oracle import coracle as co
+    from tests.helpers import scale_plan_from_slopes
+    z = load_case("case_deletion_5k")
+    op, val = scale_plan_from_slopes(z["slopes"])
+    hcm = co.scale_blocks(z["fusion_matrix"], z["block_index"], op, val)
+    kept = co.remove_gaps_index(hcm)
+    G = hcm[np.ix_(kept, kept)]
+    n = G.shape[0]
+    band = np.zeros((n, 414))
+    for d in range(min(414, n)):
+        band[:n - d, d] = np.diagonal(G, d)
+    ctx = _lib.Context.get(0)
+    forest = load_forest(os.path.join(GOLDEN, "forest_w6.joblib"), ctx)
+    b = ScoreBatch(4, 400, ctx)
+    b.add_dense(G)
+    b.add_band(band)
+    b.score(forest, z["expected"], float(z["prob"]))
+    i0, j0, p0 = b.scored(0)
+    i1, j1, p1 = b.scored(1)
+    assert np.array_equal(i0, i1) and np.array_equal(j0, j1) and np.array_equal(p0, p1)
+    assert np.array_equal(p0, z["probas"])
+    b.close()
+
+
+def test_pipeline_5kb_matches_port_live():
+    """5 kb: scipy's peak-distance filter is active (distance 3) and numpy's tie order matters;
+    pipeline() must still reproduce the port (which calls scipy/numpy on this machine)."""
+    from neoloopfinder_b200.cli import pipeline
+    from neoloopfinder_b200.synth import SMALL_CHROMSIZES
+    from neoloopfinder_b200.util import calculate_expected
+    from oracle import pyport
+    sv = ("chr1", 4_000_000, "+", "chr3", 2_500_000, "-")
+    clr = SyntheticCooler(binsize=5000, chromsizes=SMALL_CHROMSIZES, seed=31, svs=[sv], amplitude=127.5)
+    lines = {"C0": "translocation,1,4000000,+,3,2500000,-\t1,3600000\t3,2900000"}
+    exp = calculate_expected(clr, list(SMALL_CHROMSIZES), maxdis=5000000, balance="sweight", nproc=1)
+    model = {5000: os.path.join(GOLDEN, "forest_w6.joblib")}
+    want = pyport.pipeline(clr, "C0", lines, 450000, "sweight", 0.12, 2, False, model, exp)
+    got = pipeline(clr, "C0", lines, 450000, "sweight", 0.12, 2, False, model, exp)
+    assert got == want and len(want) > 20
+
+
+def test_cli_two_resolutions(tmp_path):
+    """The neoloop-caller command line end to end (two resolutions, combine_annotations, output
+    file) against the Python port driven the same way."""
+    from neoloopfinder_b200.cli import run
+    from neoloopfinder_b200.synth import SMALL_CHROMSIZES
+    from oracle import pyport
+    svs = [("chr2", 4_000_000, "-", "chr4", 3_000_000, "+")]
+    specs = {}
+    for res, amp in ((10000, 255.0), (5000, 127.5)):
+        clr = SyntheticCooler(binsize=res, chromsizes=SMALL_CHROMSIZES, seed=41, svs=svs, amplitude=amp)
+        path = tmp_path / f"map_{res}.json"
+        clr.save(str(path))
+        specs[res] = (str(path), clr)
+    asm = tmp_path / "test.assemblies.txt"
+    asm.write_text("C0\ttranslocation,2,4000000,-,4,3000000,+\t2,4400000\t4,2600000\n")
+    out = tmp_path / "loops.txt"
+    model = os.path.join(GOLDEN, "forest_w6.joblib")
+    run(["-O", str(out), "-H", specs[10000][0], specs[5000][0], "--assembly", str(asm), "-R", "400000",
+         "--prob", "0.2", "--model", model, model, "--logFile", str(tmp_path / "log.txt"),
+         "--cachefolder", str(tmp_path / "cache")])
+    got = [ln.rstrip("\n").split("\t") for ln in open(out)]
+    # reference flow with the port
+    byres = {}
+    lines = {"C0": "translocation,2,4000000,-,4,3000000,+\t2,4400000\t4,2600000"}
+    for res in (10000, 5000):
+        clr = specs[res][1]
+        chroms = [c for c in clr.chromnames]
+        exp = pyport.calculate_expected(clr, chroms, maxdis=5000000, balance="sweight")
+        r = pyport.pipeline(clr, "C0", lines, 400000, "sweight", 0.2, 2, False, {res: model}, exp)
+        cache = {}
+        for key in r:
+            cache.setdefault(key, []).append(r[key])
+        byres[res] = cache
+    want = pyport.combine_annotations(byres)
+    assert len(want) > 0
+    norm = lambda rows: sorted((tuple(r[:6]), tuple(sorted(zip(*[iter(r[6].split(","))] * 3)))) for r in rows)
+    assert norm(got) == norm(want)
