@@ -107,7 +107,7 @@ def _cpu_score_one(args):
     return int(cap.get("n_scored", 0))
 
 
-CPU_SLICE = 20000      # candidates per work unit (about 6 s of one core)
+CPU_SLICE = 50000      # candidates per work unit (about 13 s of one core)
 
 
 def cpu_work_units(items, expected, n_units):
@@ -203,7 +203,7 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     clr, lines, expected = build_assemblies(0, N_ASSEMBLIES)
     items = gap_free_matrices_cpu(clr, lines, expected, 6)
-    workers = min(cores, 6 * len(items))           # a 10 kb assembly has ~7 slices of CPU_SLICE candidates
+    workers = min(cores, 3 * len(items))           # a 10 kb assembly has ~3 slices of CPU_SLICE candidates
     if args.warmup > 0:
         from joblib import Parallel, delayed
         Parallel(n_jobs=workers)(delayed(int)(k) for k in range(workers))       # start the loky workers
@@ -424,7 +424,7 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             items = [(G, None, ch) for G, ch in zip(host_mats[:8], chains[:8])]
-            workers = min(cores, 6 * len(items))
+            workers = min(cores, 3 * len(items))
             rate, pix, secs = cpu_reference_rate(items, expected, workers)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": workers, "kind": "port",
