@@ -197,41 +197,57 @@ class complexSV(Fusion):
         """Per-block-pair slopes against the global expected and the rescaled matrix
         (assembly.py:495-571).  GPU: masked diagonal means (once, to 2 Mb: the reference's six
         maxdis values are prefixes of it), rescale, symmetrise/triu.  Host: the regressions."""
+        tasks = self.regression_tasks()
+        self.apply_regressions([self.linear_regression(le, self.expected, min_samples=5) for le in tasks])
+
+    def regression_tasks(self):
+        """First half: diagonal means on the GPU, then the list of DISTINCT regression inputs
+        (one local-expected dictionary per block pair and distinct maxdis prefix).  The fits are
+        independent, tiny and host-bound (HuberRegressor / L-BFGS), so a caller may farm them out to
+        worker processes and hand the results to ``apply_regressions`` in the same order."""
         asm = self._device_assembly()
         nb = len(self.blocks)
         res = self.res
         maxdiag = _MAXDIS_LADDER[-1] // res
         mean, _cnt = asm.diag_means(maxdiag, mink=3)
-
-        slopes, exps, pair_binary = {}, {}, {}
+        self._reg_plan = []          # per pair: (j1, j2, [task index per ladder step], last local_exp)
+        tasks = []
         p = 0
         for j1 in range(nb):
             for j2 in range(j1, nb):
                 row = mean[p]
                 p += 1
                 kept = np.where(~np.isnan(row))[0]
-                rs, ss, ws = [], [], []
-                memo = {}
+                memo, steps = {}, []
                 local_exp = {}
                 for maxdis in _MAXDIS_LADDER:
                     upto = kept[kept <= maxdis // res]
                     local_exp = {int(i): row[i] for i in upto}
                     key = len(upto)                      # prefixes: same length <=> same dictionary
                     if key not in memo:
-                        memo[key] = self.linear_regression(local_exp, self.expected, min_samples=5)
-                    r, s, w = memo[key]
-                    rs.append(r)
-                    ss.append(s)
-                    ws.append(w)
-                rs = np.r_[rs]
-                r = rs.max()
-                s = ss[rs.argmax()]
-                if any(ws):
-                    pair_binary[(j1, j2)] = 1 if (r > 0.6 and s > 0) else 0
-                else:
-                    pair_binary[(j1, j2)] = 1
-                slopes[(j1, j2)] = [r, s]
-                exps[(j1, j2)] = local_exp
+                        memo[key] = len(tasks)
+                        tasks.append(local_exp)
+                    steps.append(memo[key])
+                self._reg_plan.append((j1, j2, steps, local_exp))
+        return tasks
+
+    def apply_regressions(self, results):
+        """Second half: pick the best fit per pair, rescale on the GPU (assembly.py:520-571)."""
+        asm = self._device_assembly()
+        nb = len(self.blocks)
+        slopes, exps, pair_binary = {}, {}, {}
+        for j1, j2, steps, local_exp in self._reg_plan:
+            rs = np.r_[[results[k][0] for k in steps]]
+            ss = [results[k][1] for k in steps]
+            ws = [results[k][2] for k in steps]
+            r = rs.max()
+            s = ss[rs.argmax()]
+            if any(ws):
+                pair_binary[(j1, j2)] = 1 if (r > 0.6 and s > 0) else 0
+            else:
+                pair_binary[(j1, j2)] = 1
+            slopes[(j1, j2)] = [r, s]
+            exps[(j1, j2)] = local_exp
 
         op = np.zeros((nb, nb), dtype=np.int32)
         val = np.ones((nb, nb), dtype=np.float64)

@@ -23,7 +23,7 @@ from .scoring import DeviceAssembly, ScoreBatch, local_clustering_gpu, pool_buck
 
 log = logging.getLogger(__name__)
 
-__all__ = ["check_increasing", "clean_inputs", "Fusion", "Peakachu", "combine_annotations"]
+__all__ = ["check_increasing", "clean_inputs", "linear_regression_fit", "Fusion", "Peakachu", "combine_annotations"]
 
 
 def check_increasing(x, y):
@@ -61,6 +61,35 @@ def clean_inputs(Xi, X, Y, increasing_bool):
     return X[si:], Y[si:]
 
 
+def linear_regression_fit(exp1, exp2, min_samples=5):
+    """Slope of local vs global expected with a Huber fit (neoloop/callers.py:370-412).
+    Module-level so that it can be shipped to worker processes."""
+    from sklearn.linear_model import HuberRegressor
+    keys = [i for i in sorted(exp1) if i in exp2]
+    Xi = np.r_[keys]
+    X = np.r_[[exp2[i] for i in keys]]
+    Y = np.r_[[exp1[i] for i in keys]]
+    if X.size < min_samples:
+        return 0, 0, False
+    warning, increasing = check_increasing(Xi, Y)
+    Xc, Yc = clean_inputs(Xi, X, Y, increasing)
+    rscores, slopes = [], []
+    for X_, Y_ in ((X, Y), (Xc, Yc)):
+        X2 = X_[:, np.newaxis]
+        huber = HuberRegressor().fit(X2, Y_)
+        inliers = np.logical_not(huber.outliers_)
+        if inliers.sum() < min_samples:
+            r, s = 0, 0
+        else:
+            r = huber.score(X2[inliers], Y_[inliers])
+            s = huber.coef_[0]
+        rscores.append(r)
+        slopes.append(s)
+    rscores = np.r_[rscores]
+    slopes = np.r_[slopes]
+    return rscores.max(), slopes[np.argmax(rscores)], warning
+
+
 class Fusion(object):
     """The part of the reference's ``Fusion`` that the neoloop-caller path inherits."""
 
@@ -76,30 +105,7 @@ class Fusion(object):
 
     def linear_regression(self, exp1, exp2, min_samples=5):
         """Slope of local vs global expected with a Huber fit (neoloop/callers.py:370-412)."""
-        from sklearn.linear_model import HuberRegressor
-        keys = [i for i in sorted(exp1) if i in exp2]
-        Xi = np.r_[keys]
-        X = np.r_[[exp2[i] for i in keys]]
-        Y = np.r_[[exp1[i] for i in keys]]
-        if X.size < min_samples:
-            return 0, 0, False
-        warning, increasing = check_increasing(Xi, Y)
-        Xc, Yc = clean_inputs(Xi, X, Y, increasing)
-        rscores, slopes = [], []
-        for X_, Y_ in ((X, Y), (Xc, Yc)):
-            X2 = X_[:, np.newaxis]
-            huber = HuberRegressor().fit(X2, Y_)
-            inliers = np.logical_not(huber.outliers_)
-            if inliers.sum() < min_samples:
-                r, s = 0, 0
-            else:
-                r = huber.score(X2[inliers], Y_[inliers])
-                s = huber.coef_[0]
-            rscores.append(r)
-            slopes.append(s)
-        rscores = np.r_[rscores]
-        slopes = np.r_[slopes]
-        return rscores.max(), slopes[np.argmax(rscores)], warning
+        return linear_regression_fit(exp1, exp2, min_samples)
 
     def remove_gaps(self):
         """Gap-free matrix and gap-free -> original index map (neoloop/callers.py:504-522).

@@ -37,9 +37,18 @@ log = logging.getLogger(__name__)
 from .sharding import assembly_weight, estimate_pixels, lpt_shards  # noqa: E402,F401 (re-exported)
 
 
+def _regress_chunk(tasks, expected):
+    from .callers import linear_regression_fit
+    return [linear_regression_fit(le, expected, 5) for le in tasks]
+
+
 def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model, expected, ctx=None,
-                    stats=None):
-    """pipeline() for many assemblies on one GPU, batched.  Returns {ID: final_dict or None}."""
+                    stats=None, nproc=1):
+    """pipeline() for many assemblies on one GPU, batched.  Returns {ID: final_dict or None}.
+
+    The per-block-pair regressions (HuberRegressor, host-bound, ~5 ms each, ~18 per simple
+    assembly) dominate the wall time once the scoring runs on the GPU; with nproc > 1 they are
+    farmed out to loky worker processes, as the reference does for whole assemblies."""
     from . import _lib
     from .assembly import complexSV
     from .forest import DeviceForest, load_forest
@@ -58,11 +67,25 @@ def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, mod
             out[ID] = None                         # invalid assembly (scripts/neoloop-caller:196-197)
             continue
         fu._ctx = ctx
-        fu.correct_heterozygosity()
-        fu.remove_gaps()
         live.append((ID, fu))
     if not live:
         return out
+    # normalisation: diagonal means on the GPU for every assembly, then all regressions, then rescale
+    task_lists = [fu.regression_tasks() for _ID, fu in live]
+    flat = [t for tl in task_lists for t in tl]
+    if nproc > 1 and len(flat) > 8:
+        from joblib import Parallel, delayed
+        chunk = max(1, len(flat) // (nproc * 4))
+        chunks = [flat[k:k + chunk] for k in range(0, len(flat), chunk)]
+        parts = Parallel(n_jobs=nproc)(delayed(_regress_chunk)(ch, expected) for ch in chunks)
+        fitted = [r for part in parts for r in part]
+    else:
+        fitted = _regress_chunk(flat, expected)
+    k = 0
+    for (_ID, fu), tl in zip(live, task_lists):
+        fu.apply_regressions(fitted[k:k + len(tl)])
+        k += len(tl)
+        fu.remove_gaps()
     exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
     batch = ScoreBatch(4, 400, ctx)               # upper = 400*res // res (scripts/neoloop-caller:202)
     chains = []
@@ -99,7 +122,7 @@ def pipeline(clr, index, assemblies, rsize, balance, prob, mmp, nopool, models_b
 
 
 def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, nopool, model_path, expected,
-                    devices: Optional[List[int]] = None, stats=None):
+                    devices: Optional[List[int]] = None, stats=None, nproc=1):
     """All assemblies of one resolution, sharded over GPUs by assembly (no collective: the
     per-assembly results are KB-sized dictionaries merged on the host)."""
     from . import _lib
@@ -120,7 +143,7 @@ def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, 
             ctx = _lib.Context.get(dev)
             st = {} if stats is not None else None
             r = call_assemblies(clr, [ids[k] for k in idx], assemblies, rsize, balance, prob, mmp, nopool,
-                                model_path, expected, ctx, st)
+                                model_path, expected, ctx, st, max(1, nproc // len(devices)))
             results.update(r)
             if stats is not None:
                 for k, v in st.items():
@@ -300,7 +323,7 @@ def run(argv=None):
             logger.info('Done')
             stats = {}
             results = call_resolution(clr, lines, args.region_size, balance, args.prob, args.min_marginal_peaks,
-                                      args.no_clustering, models_by_res[res], expected, devices, stats)
+                                      args.no_clustering, models_by_res[res], expected, devices, stats, args.nproc)
             logger.info('Scored {0} pixels ({1} candidates, {2} above the threshold)'.format(
                 stats.get('scored', 0), stats.get('candidates', 0), stats.get('donuts', 0)))
             logger.info('Merge loops across assemblies ...')
