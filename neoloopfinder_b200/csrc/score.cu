@@ -244,8 +244,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n)
 
 template <int W>
 __global__ void __launch_bounds__(FeatCfg<W>::NT, 2)
-k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int lower, int upper,
-           int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, PixRef *__restrict__ pix,
+k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int tile_offset,
+           int lower, int upper, int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, PixRef *__restrict__ pix,
            float *__restrict__ featT, unsigned *__restrict__ slot_counter, unsigned max_slots,
            int *__restrict__ overflow, unsigned *__restrict__ nanmask)
 {
@@ -266,7 +266,7 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- tile -> (job, x0, d0)
-    int t = blockIdx.x;
+    int t = blockIdx.x + tile_offset;
     int lo = 0, hi = njobs;
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -1448,13 +1448,13 @@ NLF_EXPORT int nlf_batch_add_assembly(nlf_batch *b, nlf_assembly *a)
 NLF_EXPORT int nlf_batch_njobs(nlf_batch *b) { return b ? (int)b->jobs.size() : 0; }
 
 template <int W>
-static int launch_features(nlf_batch *b, int total_tiles, int nexp)
+static int launch_features(nlf_batch *b, int tile_offset, int n_tiles, int nexp)
 {
     nlf_ctx *c = b->ctx;
     KLaunch k(c, P_FEATURE);
-    k_features<W><<<total_tiles, FeatCfg<W>::NT, 0, c->stream>>>(
-        b->d_jobs, b->d_tile_base, (int)b->jobs.size(), b->lower, b->upper, b->pitch, b->ndp, b->ndt, b->d_exp, nexp,
-        b->d_pix, b->d_featT, b->d_group_counter, b->max_groups * 32u, b->d_overflow, b->d_nanmask);
+    k_features<W><<<n_tiles, FeatCfg<W>::NT, 0, c->stream>>>(
+        b->d_jobs, b->d_tile_base, (int)b->jobs.size(), tile_offset, b->lower, b->upper, b->pitch, b->ndp, b->ndt,
+        b->d_exp, nexp, b->d_pix, b->d_featT, b->d_group_counter, b->max_groups * 32u, b->d_overflow, b->d_nanmask);
     return NLF_OK;
 }
 
@@ -1683,25 +1683,39 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     NLF_CUDA(cudaMallocAsync(&b->d_don_v, sizeof(double) * b->don_cap, c->stream));
     rc = upload_jobs(b, w);
     if (rc) return rc;
-    const long long groups = b->total_groups;
+    // Feature memory is bounded: tiles are processed in chunks whose worst-case feature footprint
+    // (TX*32 slots of F floats per tile) stays below the budget, each chunk going through the feature
+    // and the forest kernels before the next one starts (results land in `prob` by pixel coordinates).
     const int tiles = b->total_tiles;
-    if (groups > 0xfffffff0LL) return fail(NLF_ERR_ARG, "batch too large: %lld feature groups; split the batch", groups);
+    const int TXh = (w >= 7) ? 8 : 16;
+    size_t budget_mb = 12288;
+    if (const char *e = getenv("NLF_FEATURE_BUDGET_MB")) budget_mb = (size_t)std::max(1, atoi(e));
+    const size_t slot_bytes = (size_t)F * 4 + sizeof(PixRef) + 8;
+    long long tiles_per_chunk = (long long)((budget_mb << 20) / (slot_bytes * TXh * 32));
+    tiles_per_chunk = std::max(1LL, std::min<long long>(tiles_per_chunk, tiles));
+    const int n_chunks = (int)((tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    if (n_chunks > 1 && b->keep_slots)
+        return fail(NLF_ERR_ARG, "batch needs %d feature chunks: features cannot be kept (raise NLF_FEATURE_BUDGET_MB or split the batch)", n_chunks);
+    const long long groups = tiles_per_chunk * TXh;            // 32 slots per group, TX*32 slots per tile
     b->max_groups = (unsigned)groups;
     NLF_CUDA(c->big_alloc((void **)&b->d_pix, sizeof(PixRef) * (size_t)groups * 32));
     NLF_CUDA(c->big_alloc((void **)&b->d_featT, sizeof(float) * (size_t)groups * F * 32));
     NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned), c->stream));
     NLF_CUDA(c->big_alloc((void **)&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1)));
-    NLF_CUDA(cudaMemsetAsync(b->d_nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_overflow, sizeof(int), c->stream));
-    NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
     NLF_CUDA(cudaMemsetAsync(b->d_overflow, 0, sizeof(int), c->stream));
-
-    if (w == 5) launch_features<5>(b, tiles, nexp);
-    else if (w == 6) launch_features<6>(b, tiles, nexp);
-    else launch_features<7>(b, tiles, nexp);
-    NLF_CUDA(cudaGetLastError());
-    rc = launch_forest(b, f, w, F);
-    if (rc) return rc;
+    for (int ch = 0; ch < n_chunks; ch++) {
+        const int t_off = (int)(ch * tiles_per_chunk);
+        const int t_cnt = (int)std::min<long long>(tiles_per_chunk, tiles - t_off);
+        NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
+        NLF_CUDA(cudaMemsetAsync(b->d_nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
+        if (w == 5) launch_features<5>(b, t_off, t_cnt, nexp);
+        else if (w == 6) launch_features<6>(b, t_off, t_cnt, nexp);
+        else launch_features<7>(b, t_off, t_cnt, nexp);
+        NLF_CUDA(cudaGetLastError());
+        rc = launch_forest(b, f, w, F);
+        if (rc) return rc;
+    }
     {
         KLaunch k(c, P_THRESH);
         dim3 grid(64, nj);

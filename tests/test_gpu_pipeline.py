@@ -200,3 +200,69 @@ def test_cli_two_resolutions(tmp_path):
     assert len(want) > 0
     norm = lambda rows: sorted((tuple(r[:6]), tuple(sorted(zip(*[iter(r[6].split(","))] * 3)))) for r in rows)
     assert norm(got) == norm(want)
+
+
+def test_feature_chunking_gives_identical_results(monkeypatch):
+    """A tiny feature-memory budget forces many feature/forest chunks; results must not change."""
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.forest import load_forest
+    from neoloopfinder_b200.scoring import ScoreBatch
+    from oracle import coracle as co
+    from tests.helpers import scale_plan_from_slopes
+    z = load_case("case_transloc_10k")
+    op, val = scale_plan_from_slopes(z["slopes"])
+    hcm = co.scale_blocks(z["fusion_matrix"], z["block_index"], op, val)
+    kept = co.remove_gaps_index(hcm)
+    G = hcm[np.ix_(kept, kept)]
+    ctx = _lib.Context.get(0)
+    forest = load_forest(os.path.join(GOLDEN, "forest_w6.joblib"), ctx)
+    monkeypatch.setenv("NLF_FEATURE_BUDGET_MB", "1")
+    b = ScoreBatch(4, 400, ctx)
+    b.add_dense(G)
+    b.add_dense(G)
+    b.score(forest, z["expected"], float(z["prob"]))
+    for job in (0, 1):
+        i, j, p = b.scored(job)
+        assert np.array_equal(np.stack([i, j], 1), z["clist"])
+        assert np.array_equal(p, z["probas"])
+    b.close()
+
+
+def test_long_banded_chromosome_matches_oracle():
+    """Config-4 shape: one long chromosome given as its band (n x 414), several feature chunks,
+    against the C oracle on the equivalent dense matrix."""
+    import joblib
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.forest import load_forest
+    from neoloopfinder_b200.scoring import ScoreBatch
+    from neoloopfinder_b200.synth import analytic_expected
+    from oracle import coracle as co
+    n = 2600
+    clr = SyntheticCooler(binsize=10000, chromsizes={"chr1": n * 10000}, seed=77)
+    G = clr.matrix(balance="sweight").fetch("chr1")
+    G[np.isnan(G)] = 0
+    G = np.triu(G)
+    keep = np.where(G.sum(axis=0) != 0)[0]
+    G = np.ascontiguousarray(G[np.ix_(keep, keep)])
+    m = G.shape[0]
+    band = np.zeros((m, 414))
+    for d in range(414):
+        band[:m - d, d] = np.diagonal(G, d)
+    exp = analytic_expected(clr)
+    exp_arr = np.array([exp[i] for i in sorted(exp)])
+    ctx = _lib.Context.get(0)
+    model_path = os.path.join(GOLDEN, "forest_w6.joblib")
+    forest = load_forest(model_path, ctx)
+    os.environ["NLF_FEATURE_BUDGET_MB"] = "256"
+    try:
+        b = ScoreBatch(4, 400, ctx)
+        b.add_band(band)
+        b.score(forest, exp_arr, 0.9)
+        i, j, p = b.scored(0)
+        b.close()
+    finally:
+        del os.environ["NLF_FEATURE_BUDGET_MB"]
+    cl, pr, _ = co.score_matrix(G, exp_arr, co.sklearn_forest_arrays(joblib.load(model_path)), 6)
+    assert len(pr) > 500000
+    assert np.array_equal(np.stack([i, j], 1), cl)
+    assert np.array_equal(p, pr)
