@@ -36,6 +36,7 @@ struct BucketWs {           // per-bucket workspace carved from one device alloc
     unsigned char *pool;    // [m]
     unsigned char *visited; // [m]
     unsigned char *is_final;// [m]
+    int *pr_rect, *pr_pt, *pr_sorted;   // [4m] (anchor rectangle, point) memberships
 };
 
 __device__ int d_local_maxima(const double *x, int n, int *mid)
@@ -358,6 +359,9 @@ __device__ BucketWs carve(char *base, int range, int m)
     w.pool = (unsigned char *)take(m);
     w.visited = (unsigned char *)take(m);
     w.is_final = (unsigned char *)take(m);
+    w.pr_rect = (int *)take(sizeof(int) * 4 * (size_t)m);
+    w.pr_pt = (int *)take(sizeof(int) * 4 * (size_t)m);
+    w.pr_sorted = (int *)take(sizeof(int) * 4 * (size_t)m);
     return w;
 }
 
@@ -374,6 +378,7 @@ size_t pool_ws_bytes(int range, int m)
     o += al(sizeof(int) * m) * 5;
     o += al(sizeof(int) * (m + 1));
     o += al(m) * 3;
+    o += al(sizeof(int) * 4 * (size_t)m) * 3;
     return o + 64;
 }
 
@@ -421,17 +426,66 @@ __global__ void __launch_bounds__(256) k_pool(PoolArgs A)
     int r = A.r_bp / A.res; if (r < 2) r = 2;
     unsigned char *sel = (unsigned char *)ws.outl;   // outl is only used inside d_cluster_core, after sel is consumed
     const int nxa = s_nxa, nya = s_nya;
-    for (int a = 0; a < nxa; a++)
-        for (int b = 0; b < nya; b++) {
-            const Anchor X = ws.xa[a], Y = ws.ya[b];
-            for (int k = tid; k < m; k += nt)
-                sel[k] = (pi[k] >= X.lb && pi[k] <= X.rb && pj[k] >= Y.lb && pj[k] <= Y.rb);
-            __syncthreads();
-            int cnt = blk_select_sorted(sel, m, pi, pj, val, ws.sl, nullptr);
-            __syncthreads();
-            d_cluster_core(ws.sl, cnt, r, pi, pj, ws);
-            __syncthreads();
+    // The reference walks every (x anchor, y anchor) rectangle and looks its points up
+    // (callers.py:711-720).  Rectangles are independent of each other (fresh `pool` per call,
+    // append-only results), so only the non-empty ones are visited here: every point emits the
+    // rectangles it belongs to, the (rectangle, point) pairs are sorted by rectangle and, inside a
+    // rectangle, in the reference's descending (value, (i, j)) order.
+    __shared__ int s_npairs;
+    const int cap = 4 * m;
+    if (tid == 0) s_npairs = 0;
+    __syncthreads();
+    for (int k = tid; k < m; k += nt) {
+        const int x = pi[k], y = pj[k];
+        for (int a = 0; a < nxa; a++) {
+            if (x < ws.xa[a].lb || x > ws.xa[a].rb) continue;
+            for (int b = 0; b < nya; b++) {
+                if (y < ws.ya[b].lb || y > ws.ya[b].rb) continue;
+                int pos = atomicAdd(&s_npairs, 1);
+                if (pos < cap) { ws.pr_rect[pos] = a * nya + b; ws.pr_pt[pos] = k; }
+            }
         }
+    }
+    __syncthreads();
+    const int npairs = s_npairs;
+    if (npairs <= cap) {
+        // rank sort of the pairs (all keys distinct)
+        for (int u = tid; u < npairs; u += nt) {
+            const int ru = ws.pr_rect[u], pu = ws.pr_pt[u];
+            int rank = 0;
+            for (int v = 0; v < npairs; v++) {
+                const int rv = ws.pr_rect[v];
+                rank += (rv < ru) || (rv == ru && v != u && pt_before(pi, pj, val, ws.pr_pt[v], pu));
+            }
+            ws.pr_sorted[rank] = u;
+        }
+        __syncthreads();
+        int pos = 0;
+        while (pos < npairs) {
+            const int rect = ws.pr_rect[ws.pr_sorted[pos]];
+            int end = pos + 1;
+            while (end < npairs && ws.pr_rect[ws.pr_sorted[end]] == rect) end++;
+            const int len = end - pos;
+            for (int q = tid; q < len; q += nt) ws.sl[q] = ws.pr_pt[ws.pr_sorted[pos + q]];
+            __syncthreads();
+            d_cluster_core(ws.sl, len, r, pi, pj, ws);
+            __syncthreads();
+            pos = end;
+        }
+    } else {
+        // heavily overlapping anchors: fall back to the plain double loop
+        for (int a = 0; a < nxa; a++)
+            for (int b = 0; b < nya; b++) {
+                const Anchor X = ws.xa[a], Y = ws.ya[b];
+                for (int k = tid; k < m; k += nt)
+                    sel[k] = (pi[k] >= X.lb && pi[k] <= X.rb && pj[k] >= Y.lb && pj[k] <= Y.rb);
+                __syncthreads();
+                int cnt = blk_select_sorted(sel, m, pi, pj, val, ws.sl, nullptr);
+                __syncthreads();
+                d_cluster_core(ws.sl, cnt, r, pi, pj, ws);
+                __syncthreads();
+            }
+    }
     for (int k = tid; k < m; k += nt) sel[k] = !ws.visited[k];
     __syncthreads();
     int cnt = blk_select_sorted(sel, m, pi, pj, val, ws.sl, nullptr);
