@@ -125,6 +125,10 @@ int nlf_batch_fetch_donuts_all(nlf_batch *b, long long cap, int *job, int *i, in
 /* Every scored pixel of one job in candidate order (diagonal-major, row-ascending):
  * clist and probas of Peakachu.predict.  cap = capacity of the arrays. */
 int nlf_batch_fetch_scored(nlf_batch *b, int job, long long cap, int *i, int *j, double *prob);
+/* Diagonal means and their decreasing isotonic fit (callers.py:540-551) of one job: arrays of
+ * upper+1 doubles indexed by the diagonal (entries below `lower` are NaN; means of diagonals with
+ * at most 5 entries are NaN). */
+int nlf_batch_fetch_expected(nlf_batch *b, int job, double *means, double *e);
 /* Peakachu.ridx / cidx (callers.py:553-570) of one job. */
 int nlf_batch_fetch_candidates(nlf_batch *b, int job, long long cap, int *ridx, int *cidx);
 /* float32 feature rows (what sklearn sees after its cast) of the scored pixels of one job, in

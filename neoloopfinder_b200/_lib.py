@@ -64,6 +64,7 @@ _SIGNATURES = {
     "nlf_batch_fetch_donuts": (C.c_int, [vp, C.c_int, ip, ip, dp, dp]),
     "nlf_batch_fetch_donuts_all": (C.c_int, [vp, C.c_longlong, ip, ip, ip, dp, dp, llp]),
     "nlf_batch_fetch_scored": (C.c_int, [vp, C.c_int, C.c_longlong, ip, ip, dp]),
+    "nlf_batch_fetch_expected": (C.c_int, [vp, C.c_int, dp, dp]),
     "nlf_batch_fetch_candidates": (C.c_int, [vp, C.c_int, C.c_longlong, ip, ip]),
     "nlf_batch_fetch_features32": (C.c_int, [vp, C.c_int, C.c_longlong, fp]),
     "nlf_batch_getwindow": (C.c_int, [vp, C.c_int, ip, ip, C.c_longlong, C.c_int, dp, C.c_int, dp, C.c_int, dp, ip, llp]),

@@ -96,23 +96,79 @@ __global__ void k_band_copy(const double *__restrict__ src, int n, int src_pitch
 }
 
 // =============================================================================================
-// K5a per-diagonal means (numpy pairwise order): one thread per (job, diagonal); consecutive
-// threads read consecutive addresses of a band row.
+// K5a per-diagonal means in numpy's pairwise order, 8 lanes per diagonal.
+// numpy splits n > 128 at n/2 - (n/2)%8, so every leaf starts at a multiple of 8 and only the last
+// leaf has a ragged tail: inside a leaf, element e feeds accumulator e%8.  Lane j of an 8-lane group
+// therefore owns accumulator j of every leaf (rows off+8i+j), the combine ((r0+r1)+(r2+r3))+((r4+r5)+
+// (r6+r7)) is a 3-step xor butterfly (fp add is commutative, the association is numpy's), and the
+// recursion over leaves is replayed identically by the 8 lanes.  A warp serves 4 neighbouring
+// diagonals: each load instruction touches 8 rows x 32 contiguous bytes.
 // =============================================================================================
-__global__ void k_diag_means(const JobDev *__restrict__ jobs, int lower, int upper, int pitch)
+__global__ void __launch_bounds__(256) k_diag_means(const JobDev *__restrict__ jobs, int lower, int upper, int pitch)
 {
     const JobDev J = jobs[blockIdx.y];
-    int d = lower + blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, j = lane & 7;
+    const int d = lower + blockIdx.x * 32 + warp * 4 + g;
     if (d > upper) return;
-    int len = J.n - d;
+    const unsigned gmask = 0xffu << (8 * g);
+    const int len = J.n - d;
     double m = __longlong_as_double(0x7ff8000000000000LL);
     if (len > 5) {
         const double *base = J.band + d;
-        size_t p = (size_t)pitch;
-        double s = np_pairwise_sum([=](int i) { return base[(size_t)i * p]; }, len);
+        const size_t p = (size_t)pitch;
+        auto ld = [&](int e) { return base[(size_t)e * p]; };
+        auto leaf = [&](int off, int cnt) -> double {
+            if (cnt < 8) {
+                double r = -0.0;
+                for (int i = 0; i < cnt; i++) r = __dadd_rn(r, ld(off + i));
+                return r;
+            }
+            const int groups = cnt >> 3;
+            double r = ld(off + j);
+            int i = 1;
+            for (; i + 4 <= groups; i += 4) {
+                double a0 = ld(off + 8 * i + j), a1 = ld(off + 8 * (i + 1) + j), a2 = ld(off + 8 * (i + 2) + j),
+                       a3 = ld(off + 8 * (i + 3) + j);
+                r = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r, a0), a1), a2), a3);
+            }
+            for (; i < groups; i++) r = __dadd_rn(r, ld(off + 8 * i + j));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+            for (int e = groups * 8; e < cnt; e++) r = __dadd_rn(r, ld(off + e));
+            return r;
+        };
+        double s;
+        if (len <= 128) {
+            s = leaf(0, len);
+        } else {
+            int st_off[48], st_n[48];      // st_n < 0 marks a "combine" entry
+            double vs[26];
+            int sp = 0, vp = 0;
+            st_off[sp] = 0; st_n[sp] = len; sp++;
+            while (sp) {
+                sp--;
+                const int o = st_off[sp], mm = st_n[sp];
+                if (mm < 0) {
+                    const double r = vs[--vp];
+                    const double l = vs[--vp];
+                    vs[vp++] = __dadd_rn(l, r);
+                } else if (mm <= 128) {
+                    vs[vp++] = leaf(o, mm);
+                } else {
+                    int n2 = mm / 2;
+                    n2 -= n2 % 8;
+                    st_off[sp] = 0; st_n[sp] = -1; sp++;
+                    st_off[sp] = o + n2; st_n[sp] = mm - n2; sp++;
+                    st_off[sp] = o; st_n[sp] = n2; sp++;
+                }
+            }
+            s = vs[0];
+        }
         m = __ddiv_rn(s, (double)len);
     }
-    J.means[d] = m;
+    if (j == 0) J.means[d] = m;
 }
 
 // K5b isotonic (decreasing) fit of the means: scipy's PAVA (pava_pybind.cpp) on the reversed
@@ -1621,8 +1677,8 @@ static int batch_prepare(nlf_batch *b)
     if (rc) return rc;
     {
         KLaunch k(c, P_DIAG);
-        dim3 grid((b->upper - b->lower + 1 + 63) / 64, nj);
-        k_diag_means<<<grid, 64, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->pitch);
+        dim3 grid((b->upper - b->lower + 1 + 31) / 32, nj);
+        k_diag_means<<<grid, 256, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->pitch);
     }
     {
         KLaunch k(c, P_DIAG);
@@ -1822,6 +1878,22 @@ NLF_EXPORT int nlf_batch_fetch_donuts(nlf_batch *b, int job, int *i, int *j, dou
         prob[k] = b->h_don_p[idx[k]];
         value[k] = b->h_don_v[idx[k]];
     }
+    return NLF_OK;
+}
+
+// Per-diagonal means (NaN where the diagonal has <= 5 entries) and the isotonic expected of
+// Peakachu.get_candidates for one job: arrays of upper+1 doubles indexed by the diagonal.
+NLF_EXPORT int nlf_batch_fetch_expected(nlf_batch *b, int job, double *means, double *e)
+{
+    if (!b || job < 0 || job >= (int)b->jobs.size()) return fail(NLF_ERR_ARG, "nlf_batch_fetch_expected: bad job");
+    int rc = batch_sync_counts(b);
+    if (rc) return rc;
+    nlf_ctx *c = b->ctx;
+    const int up1 = b->upper + 2;
+    const double *sc = b->d_scratch + (size_t)job * 4 * up1;
+    if (means) NLF_CUDA(cudaMemcpyAsync(means, sc, sizeof(double) * (b->upper + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (e) NLF_CUDA(cudaMemcpyAsync(e, sc + up1, sizeof(double) * (b->upper + 1), cudaMemcpyDeviceToHost, c->stream));
+    NLF_CUDA(cudaStreamSynchronize(c->stream));
     return NLF_OK;
 }
 

@@ -197,6 +197,12 @@ class ScoreBatch:
         check(_lib.load().nlf_batch_fetch_candidates(self.h, job, m, ptr(r, C.c_int), ptr(c, C.c_int)))
         return r, c
 
+    def expected(self, job: int):
+        """(diagonal means, isotonic expected) of get_candidates, indexed by the diagonal."""
+        means = np.empty(self.upper + 1); e = np.empty(self.upper + 1)
+        check(_lib.load().nlf_batch_fetch_expected(self.h, job, ptr(means, C.c_double), ptr(e, C.c_double)))
+        return means, e
+
     def features32(self, job: int):
         m = int(self.counts()[1][job])
         F = (2 * self.w + 1) ** 2

@@ -174,3 +174,34 @@ def test_constant_windows_give_nan_features_like_sklearn(gpu, forests, models):
     assert np.array_equal(p, pr)
     assert np.array_equal(p, model.predict_proba(fea32)[:, 1])
     batch.close()
+
+
+@pytest.mark.parametrize("n", [9, 10, 40, 133, 300, 777, 2100])
+def test_diagonal_means_and_isotonic_bit_exact(n, gpu):
+    """K5: every diagonal mean equals numpy's (pairwise order) and the expected equals sklearn's
+    IsotonicRegression(increasing=False, out_of_bounds='clip') prediction, bit for bit."""
+    from sklearn.isotonic import IsotonicRegression
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.scoring import ScoreBatch
+    rng = np.random.default_rng(n)
+    G = np.triu(rng.random((n, n)) * np.exp(-np.abs(np.subtract.outer(np.arange(n), np.arange(n))) / 40.0))
+    G[rng.random((n, n)) < 0.3] = 0.0
+    batch = ScoreBatch(4, 400, gpu)
+    batch.add_dense(G)
+    if n - 4 <= 5:
+        with pytest.raises(_lib.NLFError):
+            batch.counts()
+        batch.close()
+        return
+    means, e = batch.expected(0)
+    idx, obs = [], []
+    for d in range(4, 401):
+        diag = np.diagonal(G, d) if d < n else np.zeros(0)
+        if diag.size > 5:
+            assert means[d] == diag.mean(), d
+            idx.append(d); obs.append(diag.mean())
+        else:
+            assert np.isnan(means[d])
+    ref = IsotonicRegression(increasing=False, out_of_bounds="clip").fit(np.r_[idx], np.r_[obs]).predict(np.arange(4, 401))
+    assert np.array_equal(e[4:401], ref)
+    batch.close()
