@@ -175,20 +175,25 @@ __global__ void __launch_bounds__(256) k_diag_means(const JobDev *__restrict__ j
 // sequence, one thread per job (<= upper-lower+1 points).  e[d] = fit[min(d, last)].
 __global__ void k_isotonic(const JobDev *__restrict__ jobs, int lower, int upper)
 {
-    if (threadIdx.x != 0) return;
+    // work arrays in shared memory (the fit is a short, strictly sequential scan: latency matters)
+    extern __shared__ __align__(16) unsigned char iso_raw[];
     const JobDev J = jobs[blockIdx.x];
-    int last = min(upper, J.n - 6);          // diagonals lower..last have more than 5 entries
-    long long m = (long long)last - lower + 1;
-    if (m <= 0) { atomicExch(J.status, NLF_ERR_EMPTY_FIT); return; }
-    double *x = J.e;                         // reuse e[0..m) as the PAVA work array
-    double *w = J.pava_w;
-    long long *r = J.pava_r;
-    for (long long i = 0; i < m; i++) { x[i] = J.means[last - i]; w[i] = 1.0; }   // reversed
-    if (m > 1) {
+    const int last = min(upper, J.n - 6);    // diagonals lower..last have more than 5 entries
+    const long long m = (long long)last - lower + 1;
+    double *x = reinterpret_cast<double *>(iso_raw);
+    double *w = x + (upper + 2);
+    int *r = reinterpret_cast<int *>(w + (upper + 2));
+    if (m <= 0) {
+        if (threadIdx.x == 0) atomicExch(J.status, NLF_ERR_EMPTY_FIT);
+        return;
+    }
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) { x[i] = J.means[last - i]; w[i] = 1.0; }   // reversed
+    __syncthreads();
+    if (threadIdx.x == 0 && m > 1) {
         r[0] = 0; r[1] = 1;
-        long long b = 0;
+        int b = 0;
         double xb_prev = x[0], wb_prev = w[0];
-        for (long long i = 1; i < m; ++i) {
+        for (int i = 1; i < (int)m; ++i) {
             b++;
             double xb = x[i], wb = w[i], sb = 0;
             if (xb_prev >= xb) {
@@ -196,7 +201,7 @@ __global__ void k_isotonic(const JobDev *__restrict__ jobs, int lower, int upper
                 sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
                 wb = __dadd_rn(wb, wb_prev);
                 xb = __ddiv_rn(sb, wb);
-                while (i < m - 1 && xb >= x[i + 1]) {
+                while (i < (int)m - 1 && xb >= x[i + 1]) {
                     i++;
                     sb = __dadd_rn(sb, __dmul_rn(w[i], x[i]));
                     wb = __dadd_rn(wb, w[i]);
@@ -213,22 +218,22 @@ __global__ void k_isotonic(const JobDev *__restrict__ jobs, int lower, int upper
             w[b] = wb_prev = wb;
             r[b + 1] = i + 1;
         }
-        long long f = m - 1;
-        for (long long k = b; k >= 0; --k) {
-            long long t = r[k];
-            double xk = x[k];
-            for (long long i = f; i >= t; --i) x[i] = xk;
+        int f = (int)m - 1;
+        for (int k = b; k >= 0; --k) {
+            const int t = r[k];
+            const double xk = x[k];
+            for (int i = f; i >= t; --i) x[i] = xk;
             f = t - 1;
         }
     }
-    // un-reverse into w (scratch), then publish e[d] with out_of_bounds='clip'
-    for (long long i = 0; i < m; i++) w[i] = x[m - 1 - i];
-    for (int d = upper; d >= 0; d--) {
+    __syncthreads();
+    // un-reverse and publish e[d] with out_of_bounds='clip'
+    for (int d = threadIdx.x; d <= upper; d += blockDim.x) {
         double v = __longlong_as_double(0x7ff8000000000000LL);
         if (d >= lower) {
             long long k = d - lower;
             if (k > m - 1) k = m - 1;
-            v = w[k];
+            v = x[m - 1 - k];
         }
         J.e[d] = v;
     }
@@ -1682,7 +1687,7 @@ static int batch_prepare(nlf_batch *b)
     }
     {
         KLaunch k(c, P_DIAG);
-        k_isotonic<<<nj, 32, 0, c->stream>>>(b->d_jobs, b->lower, b->upper);
+        k_isotonic<<<nj, 128, (size_t)(b->upper + 2) * 20, c->stream>>>(b->d_jobs, b->lower, b->upper);
     }
     {
         KLaunch k(c, P_THRESH);
