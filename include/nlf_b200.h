@@ -89,6 +89,14 @@ int nlf_assembly_fetch_hcm(nlf_assembly *a, double *out);       /* n  x n  (comp
 int nlf_assembly_fetch_gap_free(nlf_assembly *a, double *out);  /* n' x n' (Fusion.gap_free)    */
 int nlf_assembly_destroy(nlf_assembly *a);
 
+/* ---- per-sample prologue: replaces util._prepare_core (neoloop/util.py:403-428) for one
+ *      chromosome given as its band (band[r*nd + i] = balanced M[r, r+i], i < nd = maxdis+1):
+ *      sum_out[i] / cnt_out[i] = hic.diagonal(i)[valid].sum() / .size with valid[r] = weight of bin r
+ *      finite and > 0 (numpy summation order).  calculate_expected's reduction over chromosomes and
+ *      its isotonic fit (util.py:449-466) stay on the host. ------------------------------------ */
+int nlf_expected_diagonals(nlf_ctx *ctx, const double *band, int n, int nd, const uint8_t *valid,
+                           double *sum_out, long long *cnt_out);
+
 /* ---- scoring: replaces Peakachu.__init__/get_candidates/getwindow/predict up to the
  *      Donuts dictionary (neoloop/callers.py:527-628) and util.distance_normalize /
  *      distance_normaize_core / image_normalize (neoloop/util.py:470-524) for a BATCH of

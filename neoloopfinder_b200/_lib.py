@@ -54,6 +54,7 @@ _SIGNATURES = {
     "nlf_assembly_fetch_hcm": (C.c_int, [vp, dp]),
     "nlf_assembly_fetch_gap_free": (C.c_int, [vp, dp]),
     "nlf_assembly_destroy": (C.c_int, [vp]),
+    "nlf_expected_diagonals": (C.c_int, [vp, dp, C.c_int, C.c_int, u8p, dp, llp]),
     "nlf_batch_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
     "nlf_batch_add_dense": (C.c_int, [vp, dp, C.c_int]),
     "nlf_batch_add_assembly": (C.c_int, [vp, vp]),

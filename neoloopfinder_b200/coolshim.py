@@ -443,8 +443,8 @@ class SyntheticCooler(_CoolerBase):
     def fetch_band(self, chrom, ndiag: int, balance="sweight", row_chunk: int = 8192) -> np.ndarray:
         """Upper band of one chromosome without ever forming the dense matrix:
         band[i, d] = balanced contact of bins (i, i+d), d < ndiag (0 beyond the chromosome end,
-        0 where a weight is NaN).  Same pixels as ``matrix(...).fetch(chrom)`` (SV-induced contacts
-        are not added here: genome-wide scoring treats chromosomes as trivial assemblies)."""
+        0 where a weight is NaN).  Same pixels as ``matrix(...).fetch(chrom)``, including the
+        contacts induced by intra-chromosomal SVs."""
         n = self._nbins(chrom)
         off = self._offsets[chrom]
         a, b = self._chrom_loops(chrom)
@@ -464,6 +464,20 @@ class SyntheticCooler(_CoolerBase):
                         r, c = aa + da, bb + db
                         if lo <= r < hi and r <= c < n and c - r < ndiag:
                             lam[r - lo, c - r] += self.loop_strength * (1.0 if (da == 0 and db == 0) else 0.5)
+            res = self.binsize
+            for sv in self.svs:
+                sc1, p1, s1, sc2, p2, s2 = sv[:6]
+                if sc1 != chrom or sc2 != chrom:
+                    continue
+                frac = float(sv[6]) if len(sv) > 6 else self.sv_fraction
+                for (A, B) in (((p1, s1), (p2, s2)), ((p2, s2), (p1, s1))):
+                    bpA, bpB = int(A[0]) // res, int(B[0]) // res
+                    da = (bpA - i) if A[1] == "+" else (i - bpA)
+                    db = (bpB - j) if B[1] == "+" else (j - bpB)
+                    ok = (da >= 0) & (db >= 0) & inside
+                    dist = da + db + 1
+                    ok = ok & (dist <= self.band_bins)
+                    lam += np.where(ok, frac * self.amplitude / np.where(ok, dist + 1.0, 1.0), 0.0)
             gi = (i + off).astype(np.uint64)
             gj = (np.minimum(j, n - 1) + off).astype(np.uint64)
             with np.errstate(over="ignore"):

@@ -36,6 +36,59 @@ inline int fail(int code, const char *fmt, ...)
 
 enum ProfClass { P_BANDIFY = 0, P_DIAG = 1, P_FEATURE = 2, P_FOREST = 3, P_THRESH = 4, P_NORM = 5, P_POOL = 6, P_NCLASS = 8 };
 
+// numpy pairwise sum of ld(0..len-1) computed by an aligned group of 8 lanes (lane j = accumulator j
+// of every leaf); every lane of the group returns the sum.  numpy splits n > 128 at n/2 - (n/2)%8, so
+// leaves start at multiples of 8 and only the last one has a ragged tail; the 8-accumulator combine
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is an xor butterfly (addition commutes, the association is kept).
+template <typename Load>
+__device__ double np_pairwise_sum_group8(Load ld, int len, int j, unsigned gmask)
+{
+    auto leaf = [&](int off, int cnt) -> double {
+        if (cnt < 8) {
+            double r = -0.0;
+            for (int i = 0; i < cnt; i++) r = __dadd_rn(r, ld(off + i));
+            return r;
+        }
+        const int groups = cnt >> 3;
+        double r = ld(off + j);
+        int i = 1;
+        for (; i + 4 <= groups; i += 4) {
+            double a0 = ld(off + 8 * i + j), a1 = ld(off + 8 * (i + 1) + j), a2 = ld(off + 8 * (i + 2) + j),
+                   a3 = ld(off + 8 * (i + 3) + j);
+            r = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r, a0), a1), a2), a3);
+        }
+        for (; i < groups; i++) r = __dadd_rn(r, ld(off + 8 * i + j));
+        r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+        r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+        r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+        for (int e = groups * 8; e < cnt; e++) r = __dadd_rn(r, ld(off + e));
+        return r;
+    };
+    if (len <= 128) return leaf(0, len);
+    int st_off[48], st_n[48];      // st_n < 0 marks a "combine" entry
+    double vs[26];
+    int sp = 0, vp = 0;
+    st_off[sp] = 0; st_n[sp] = len; sp++;
+    while (sp) {
+        sp--;
+        const int o = st_off[sp], mm = st_n[sp];
+        if (mm < 0) {
+            const double r = vs[--vp];
+            const double l = vs[--vp];
+            vs[vp++] = __dadd_rn(l, r);
+        } else if (mm <= 128) {
+            vs[vp++] = leaf(o, mm);
+        } else {
+            int n2 = mm / 2;
+            n2 -= n2 % 8;
+            st_off[sp] = 0; st_n[sp] = -1; sp++;
+            st_off[sp] = o + n2; st_n[sp] = mm - n2; sp++;
+            st_off[sp] = o; st_n[sp] = n2; sp++;
+        }
+    }
+    return vs[0];
+}
+
 }  // namespace nlf
 
 struct nlf_ctx {

@@ -1,10 +1,10 @@
 """Numeric helpers of the neoloop-caller path (mirror of the four hot functions of
 neoloop/util.py; the SV/peak text parsers of that module are out of scope).
 
-``calculate_expected`` is the per-sample prologue (neoloop/util.py:403-468).  It is row f-1 of
-SURVEY.md section 8 ("next"): it stays host-side numpy here, restated so that every number is
-produced by the same numpy/scipy/sklearn calls as the reference (same ``diagonal(i)[valid].sum()``
-pairwise sums, same Python-float accumulation over chromosomes, same isotonic fit).
+``calculate_expected`` is the per-sample prologue (neoloop/util.py:403-468), row f-1 of SURVEY.md
+section 8: the masked per-diagonal sums of every chromosome run on the GPU in numpy's summation
+order (``nlf_expected_diagonals``); the Python-float accumulation over chromosomes and the
+isotonic fit are the reference's own host steps.
 """
 from __future__ import annotations
 
@@ -30,36 +30,55 @@ def autosomes(chromnames: Iterable[str]):
     return keep
 
 
-def _chrom_diagonal_sums(args):
-    """One chromosome: {distance: [sum, count]} over bin pairs whose weights are both finite
-    and positive (neoloop/util.py:403-428)."""
-    clr, chrom, maxdis, balance = args
-    hic = clr.matrix(balance=balance, sparse=True).fetch(chrom)
+def chrom_band(clr, chrom, nd, balance):
+    """(band, weights): band[r, i] = balanced contact of bins (r, r+i) of one chromosome, i < nd.
+    Sources that can produce a band directly (``fetch_band``) are used as such; any other
+    cooler-like object goes through its sparse matrix (O(nnz) scatter, no per-diagonal scans)."""
     col = "weight" if isinstance(balance, bool) else balance
     weights = clr.bins().fetch(chrom)[col].values
-    ok = np.isfinite(weights) & (weights > 0)
-    n = hic.shape[0]
+    n = weights.size
+    nd = min(nd, n)
+    if hasattr(clr, "fetch_band"):
+        band = clr.fetch_band(chrom, nd, balance)
+    else:
+        coo = clr.matrix(balance=balance, sparse=True).fetch(chrom).tocoo()
+        d = coo.col - coo.row
+        ok = (d >= 0) & (d < nd)
+        band = np.zeros((n, nd), dtype=np.float64)
+        band[coo.row[ok], d[ok]] = coo.data[ok]
+    return np.ascontiguousarray(band, dtype=np.float64), weights
+
+
+def _chrom_diagonal_sums(args):
+    """One chromosome: {distance: [sum, count]} over bin pairs whose weights are both finite
+    and positive (neoloop/util.py:403-428).  The masked diagonal sums run on the GPU
+    (nlf_expected_diagonals) in numpy's summation order."""
+    import ctypes as C
+    from . import _lib
+    clr, chrom, maxdis, balance = args
+    band, weights = chrom_band(clr, chrom, maxdis + 1, balance)
+    n, nd = band.shape
+    band = np.where(np.isfinite(band), band, 0.0)         # masked out below; keep the copy finite
+    valid = np.ascontiguousarray(np.isfinite(weights) & (weights > 0), dtype=np.uint8)
+    sums = np.empty(nd, dtype=np.float64)
+    cnts = np.empty(nd, dtype=np.int64)
+    ctx = _lib.Context.get()
+    _lib.check(_lib.load().nlf_expected_diagonals(ctx.h, _lib.ptr(band, C.c_double), n, nd, _lib.ptr(valid, C.c_ubyte),
+                                                  _lib.ptr(sums, C.c_double), _lib.ptr(cnts, C.c_longlong)))
     out = {}
     for i in range(min(n - 1, maxdis) + 1):
-        valid = ok if i == 0 else ok[:-i] * ok[i:]
-        cur = hic.diagonal(i)[valid]
-        if cur.size > 0:
-            out[i] = [cur.sum(), cur.size]
+        if cnts[i] > 0:
+            out[i] = [np.float64(sums[i]), int(cnts[i])]
     return out
 
 
 def calculate_expected(clr, chroms, maxdis=5000000, balance=True, nproc=1) -> Dict[int, float]:
     """Genome-wide mean contact per genomic distance with a decreasing isotonic fit
-    (neoloop/util.py:430-468).  Returns {int distance in bins: float}."""
+    (neoloop/util.py:430-468).  Returns {int distance in bins: float}.  ``nproc`` is accepted for
+    interface compatibility; the per-chromosome scans run on the GPU one after the other."""
     from sklearn.isotonic import IsotonicRegression
     maxdis = maxdis // clr.binsize
-    jobs = [(clr, c, maxdis, balance) for c in chroms]
-    if nproc == 1:
-        per_chrom = [_chrom_diagonal_sums(j) for j in jobs]
-    else:
-        from multiprocess import Pool
-        with Pool(nproc) as pool:
-            per_chrom = pool.map(_chrom_diagonal_sums, jobs)
+    per_chrom = [_chrom_diagonal_sums((clr, c, maxdis, balance)) for c in chroms]
     raw = {}
     for i in range(maxdis + 1):
         nume = 0

@@ -266,3 +266,36 @@ def test_long_banded_chromosome_matches_oracle():
     assert len(pr) > 500000
     assert np.array_equal(np.stack([i, j], 1), cl)
     assert np.array_equal(p, pr)
+
+
+def test_calculate_expected_gpu_equals_port():
+    """Row f-1: masked per-diagonal sums on the GPU; the expected dictionary must equal the
+    reference-order port bit for bit, for a procedural map (band source) and for explicit arrays
+    (generic cooler source: sparse scatter path), balanced and raw."""
+    from neoloopfinder_b200.coolshim import ArrayCooler
+    from neoloopfinder_b200.util import calculate_expected
+    from oracle import pyport
+    sizes = {"chr1": 6_000_000, "chr2": 4_100_000, "chrX": 3_000_000}
+    clr = SyntheticCooler(binsize=10000, chromsizes=sizes, seed=9)
+    for balance in ("sweight", "weight", False):
+        want = pyport.calculate_expected(clr, ["chr1", "chr2"], maxdis=5000000, balance=balance)
+        got = calculate_expected(clr, ["chr1", "chr2"], maxdis=5000000, balance=balance)
+        assert list(got) == list(want)
+        assert all(got[k] == want[k] for k in want), balance
+    # explicit arrays (no fetch_band): small chromosomes, shorter maxdis than the chromosome
+    rng = np.random.default_rng(3)
+    blocks, weights = {}, {"weight": {}, "sweight": {}}
+    small = {"chr1": 1_230_000, "chr2": 800_000}
+    for c, size in small.items():
+        n = -(-size // 10000)
+        B = rng.poisson(3.0, size=(n, n)).astype(float)
+        B = np.triu(B) + np.triu(B, 1).T
+        blocks[(c, c)] = B
+        for col in weights:
+            w = rng.uniform(0.05, 0.15, n)
+            w[rng.random(n) < 0.05] = np.nan
+            weights[col][c] = w
+    arr = ArrayCooler(10000, small, blocks, weights)
+    want = pyport.calculate_expected(arr, list(small), maxdis=600000, balance="weight")
+    got = calculate_expected(arr, list(small), maxdis=600000, balance="weight")
+    assert all(got[k] == want[k] for k in want) and len(got) == len(want) == 61
