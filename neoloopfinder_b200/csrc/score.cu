@@ -39,8 +39,6 @@ struct JobDev {
     int *slot;
     double *means;      // [upper+1] diagonal means (NaN where the diagonal is too short)
     double *e;          // [upper+1]
-    double *pava_w;     // [upper+2] scratch
-    long long *pava_r;  // [upper+2] scratch
     int *status;        // [0] error code of the job (0 ok)
     unsigned long long *counts;  // [0] candidates, [1] scored, [2] donuts
     int *don_job, *don_i, *don_j; // Donut outputs: ONE list per batch (capacity don_cap), tagged by job
@@ -1171,7 +1169,7 @@ struct nlf_batch {
     // pools: one allocation per batch instead of a dozen per job
     int *d_status = nullptr;                 // [NLF_MAX_JOBS]
     unsigned long long *d_counts = nullptr;  // [NLF_MAX_JOBS*4 + 1]; the last word counts the Donuts
-    double *d_scratch = nullptr;             // per job: means, e, pava_w (3 * up1 doubles) and pava_r (up1 int64)
+    double *d_scratch = nullptr;             // per job: means and e (2 * up1 doubles)
     int scratch_jobs = 0;
     double *d_prob = nullptr;
     int *d_slot = nullptr;
@@ -1633,12 +1631,11 @@ static int upload_jobs(nlf_batch *b, int w)
     for (int k = 0; k < nj; k++) {
         HostJob &j = b->jobs[k];
         JobDev &d = jd[k];
-        double *sc = b->d_scratch + (size_t)k * 4 * up1;
+        double *sc = b->d_scratch + (size_t)k * 2 * up1;
         d.band = j.d_band;
         d.prob = b->d_prob ? b->d_prob + j.prob_off : nullptr;
         d.slot = b->d_slot ? b->d_slot + j.prob_off : nullptr;
-        d.means = sc; d.e = sc + up1; d.pava_w = sc + 2 * up1;
-        d.pava_r = reinterpret_cast<long long *>(sc + 3 * up1);
+        d.means = sc; d.e = sc + up1;
         d.status = b->d_status + k;
         d.counts = b->d_counts + (size_t)k * 4;
         d.don_job = b->d_don_job; d.don_i = b->d_don_i; d.don_j = b->d_don_j; d.don_p = b->d_don_p; d.don_v = b->d_don_v;
@@ -1675,7 +1672,7 @@ static int batch_prepare(nlf_batch *b)
     if (nj == 0) { b->prepared = true; return NLF_OK; }
     if (b->scratch_jobs < nj) {
         if (b->d_scratch) cudaFreeAsync(b->d_scratch, c->stream);
-        NLF_CUDA(cudaMallocAsync(&b->d_scratch, sizeof(double) * (size_t)nj * 4 * (b->upper + 2), c->stream));
+        NLF_CUDA(cudaMallocAsync(&b->d_scratch, sizeof(double) * (size_t)nj * 2 * (b->upper + 2), c->stream));
         b->scratch_jobs = nj;
     }
     int rc = upload_jobs(b, 0);
@@ -1895,7 +1892,7 @@ NLF_EXPORT int nlf_batch_fetch_expected(nlf_batch *b, int job, double *means, do
     if (rc) return rc;
     nlf_ctx *c = b->ctx;
     const int up1 = b->upper + 2;
-    const double *sc = b->d_scratch + (size_t)job * 4 * up1;
+    const double *sc = b->d_scratch + (size_t)job * 2 * up1;
     if (means) NLF_CUDA(cudaMemcpyAsync(means, sc, sizeof(double) * (b->upper + 1), cudaMemcpyDeviceToHost, c->stream));
     if (e) NLF_CUDA(cudaMemcpyAsync(e, sc + up1, sizeof(double) * (b->upper + 1), cudaMemcpyDeviceToHost, c->stream));
     NLF_CUDA(cudaStreamSynchronize(c->stream));
@@ -1941,7 +1938,7 @@ static int ordered_list(nlf_batch *b, int job, int mode, long long cap, int *oi,
     memset(&d, 0, sizeof(d));
     d.band = J.d_band; d.prob = b->d_prob ? b->d_prob + J.prob_off : nullptr;
     d.slot = b->d_slot ? b->d_slot + J.prob_off : nullptr;
-    d.e = b->d_scratch + (size_t)job * 4 * (b->upper + 2) + (b->upper + 2); d.n = J.n; d.status = b->d_status + job;
+    d.e = b->d_scratch + (size_t)job * 2 * (b->upper + 2) + (b->upper + 2); d.n = J.n; d.status = b->d_status + job;
     int *d_cnt;
     long long *d_off;
     NLF_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * nd, c->stream));

@@ -205,3 +205,56 @@ def test_diagonal_means_and_isotonic_bit_exact(n, gpu):
     ref = IsotonicRegression(increasing=False, out_of_bounds="clip").fit(np.r_[idx], np.r_[obs]).predict(np.arange(4, 401))
     assert np.array_equal(e[4:401], ref)
     batch.close()
+
+
+def _random_band_matrix(rng, n, density):
+    d = np.abs(np.subtract.outer(np.arange(n), np.arange(n)))
+    G = rng.poisson(30.0 / (d + 1.0) ** 0.8 + 0.3).astype(float) * rng.uniform(0.005, 0.02, size=(n, n))
+    G[rng.random((n, n)) > density] = 0.0
+    return np.triu(G)
+
+
+@pytest.mark.parametrize("seed,n,density,fname,nexp,zero_at", [
+    (0, 90, 0.9, "forest_w6.joblib", 501, None), (1, 230, 0.25, "forest_w6.joblib", 501, None),
+    (2, 70, 0.6, "forest_w5.joblib", 201, None), (3, 460, 0.8, "forest_w5.joblib", 201, None),
+    (4, 150, 0.7, "forest_w6.joblib", 1001, 37), (5, 640, 0.1, "forest_w6.joblib", 501, None)])
+def test_adversarial_matrices_match_oracle(seed, n, density, fname, nexp, zero_at, gpu, forests, models):
+    """Sparse maps (most windows fail the gates: ragged feature rows), NaN/inf entries, the w=5
+    model with a 201-entry expected (windows with d+2w >= 201 stay un-normalised, the boundary falls
+    inside a 32-diagonal tile), a zero in the expected table (inf -> NaN features): all bit-exact
+    against the C oracle, which tests/test_oracle_vs_reference.py pins to the live reference."""
+    from oracle import coracle as co
+    from neoloopfinder_b200.scoring import ScoreBatch
+    rng = np.random.default_rng(seed)
+    G = _random_band_matrix(rng, n, density)
+    G[5, 30] = np.nan
+    G[7, 40] = np.inf
+    exp = 0.4 / (np.arange(nexp) + 1.0)
+    if zero_at is not None:
+        exp[zero_at] = 0.0
+    forest = forests(fname)
+    batch = ScoreBatch(4, 400, gpu)
+    batch.add_dense(G)
+    batch.keep_features(True)
+    batch.score(forest, exp, 0.3)
+    r, c = batch.candidates(0)
+    orr, orc, _ = co.candidates(G)
+    assert np.array_equal(r, orr) and np.array_equal(c, orc)
+    with np.errstate(all="ignore"):
+        cl, pr, f32 = co.score_matrix(G, exp, co.sklearn_forest_arrays(models(fname)), forest.w)
+    if len(cl) < 2:
+        assert batch.counts()[1][0] == len(cl)
+        batch.close()
+        return
+    i, j, p = batch.scored(0)
+    assert np.array_equal(np.stack([i, j], 1), cl)
+    g32 = batch.features32(0)
+    nan = np.isnan(f32)
+    assert np.array_equal(np.isnan(g32), nan)                      # NaN payload bits are not part of the contract
+    assert np.array_equal(g32.view(np.uint32)[~nan], f32.view(np.uint32)[~nan])
+    assert np.array_equal(p, pr)
+    fea64, cl64 = batch.getwindow(0, orr, orc, forest.w, exp)
+    with np.errstate(all="ignore"):
+        ofea, ocl = co.getwindow(G, orr, orc, forest.w, exp)
+    assert np.array_equal(cl64, ocl) and np.array_equal(fea64, ofea, equal_nan=True)
+    batch.close()
