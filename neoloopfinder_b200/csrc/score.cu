@@ -728,6 +728,27 @@ k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off,
 #undef SM_F64
 }
 
+// shared-window loads of the forest traversal (addresses are absolute shared addresses; node
+// addresses carry a +0x40000 bias, see k_forest_pipe)
+__device__ __forceinline__ uint2 lds_node(unsigned biased)
+{
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2 + -262144];" : "=r"(v.x), "=r"(v.y) : "r"(biased));
+    return v;
+}
+__device__ __forceinline__ unsigned scaled_add4(unsigned a, unsigned b)   // 4*a + b in one instruction
+{
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ float lds_f32(unsigned addr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 // K8 (cooperative, dynamic trees, barrier-free pipeline).  Same work decomposition as
 // k_forest_dyn, but consecutive tiles overlap: there is no block barrier.  Every tile buffer has
 // a `full` mbarrier (completed by the TMA copy) and a `done` mbarrier (every thread arrives once
@@ -757,6 +778,10 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
 #define SM_U32(off) (*reinterpret_cast<unsigned *>(smem_raw + (off)))
 #define SM_F32(off) (*reinterpret_cast<float *>(smem_raw + (off)))
 #define SM_F64(off) (*reinterpret_cast<double *>(smem_raw + (off)))
+    // Staged internal node: y = 1<<31 | (shared address of the right child >> 3) << 16 | feature << 5, so
+    // that y >> 13 is that address plus the constant 0x40000 (folded into the load's immediate
+    // offset) and (y & 0x1fe0) << 2 is the byte offset of the feature row in the tile.
+    const unsigned sbase = smem_u32(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k <= ntree; k += blockDim.x)
         SM_U32(o_root + 4u * k) = (unsigned)((k < ntree) ? tree_off[t0 + k] - part_base : part_nodes);
@@ -768,7 +793,7 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
             unsigned r = (nd.y & 0x3fffffu) +
                          SM_U32(o_root + 4u * tree_of_node(reinterpret_cast<const int *>(smem_raw + o_root), ntree, k));
             unsigned feat = (nd.y >> 23) & 0xffu;
-            nd.y = 0x80000000u | ((o_nodes + (r << 3)) << 8) | feat;
+            nd.y = 0x80000000u | (((sbase + o_nodes + (r << 3)) >> 3) << 16) | (feat << 5);
         }
         SM_U2(o_nodes + 8u * k) = nd;
     }
@@ -781,7 +806,7 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = o_nodes + 8u * SM_U32(o_root + 4u * k);
+    for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = 0x40000u + sbase + o_nodes + 8u * SM_U32(o_root + 4u * k);
     __syncthreads();
     const unsigned nslots = *slot_counter;
     const unsigned ngroups = (nslots + 31u) >> 5;
@@ -807,17 +832,17 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
         mbar_wait(&full[buf], par);
         const bool active = (g * 32u + lane < nslots) && !((nanm >> lane) & 1u);
         if (active) {
-            const unsigned my = buf * tile_bytes + (unsigned)lane * 4u;
+            const unsigned my = sbase + buf * tile_bytes + (unsigned)lane * 4u;
             const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
             unsigned *cnt = reinterpret_cast<unsigned *>(smem_raw + o_cnt + buf * 128u + (unsigned)lane * 4u);
             int t = (int)atomicAdd(cnt, 1u);
             while (t < ntree) {
                 unsigned na = SM_U32(o_root + 4u * (unsigned)t);
-                uint2 nd = SM_U2(na);
+                uint2 nd = lds_node(na);
                 while ((int)nd.y < 0) {
-                    const float xv = SM_F32(my + ((nd.y & 0xffu) << 7));
-                    na = (xv <= __uint_as_float(nd.x)) ? na + 8u : ((nd.y >> 8) & 0x7fffffu);
-                    nd = SM_U2(na);
+                    const float xv = lds_f32(scaled_add4(nd.y & 0x1fe0u, my));
+                    na = (xv <= __uint_as_float(nd.x)) ? na + 8u : (nd.y >> 13);
+                    nd = lds_node(na);
                 }
                 SM_U2(lv + 256u * (unsigned)t) = nd;
                 t = (int)atomicAdd(cnt, 1u);
