@@ -387,8 +387,9 @@ def main():
             "launch_ms": feat_ms,
             "note": "k_features is fp64-issue bound and the forest kernel shared-memory bound by construction "
                     "(SURVEY.md D7: ~29 B but ~5k fp64 ops per pixel), so the HBM fraction on algorithmic bytes is small; "
-                    "the fp64-issue fraction is in roofline_fp64. traffic (ncu dram bytes) exceeds the algorithmic bytes "
-                    "because the float32 features (676 B/pixel) go through HBM between k_features and the forest kernel.",
+                    "the fp64-issue fraction is in roofline_fp64. traffic (ncu dram bytes, profiles/r01_traffic.json) exceeds the "
+                    "algorithmic bytes because the float32 features (676 B/pixel) go through HBM between k_features and the "
+                    "forest kernel.",
         }
         fp64 = {
             "kernel": "k_features", "achieved_gops": alg_ops / (feat_ms * 1e-3) / 1e9 if feat_ms else None,

@@ -756,7 +756,7 @@ __device__ __forceinline__ float lds_f32(unsigned addr)
 // next tile at once; the tile's summing warp (round robin) waits for `done`, adds the leaf values
 // in tree order, resets the tree counters and only then issues the TMA copy that refills the
 // buffer two tiles later -- which is also what protects leafv/cnt from early reuse.
-template <int NW>
+template <int NW, bool WARP_GRAB>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
               const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
@@ -831,6 +831,30 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
         const unsigned nanm_n = (gn < ngroups) ? nanmask[gn] : 0u;
         mbar_wait(&full[buf], par);
         const bool active = (g * 32u + lane < nslots) && !((nanm >> lane) & 1u);
+        if (WARP_GRAB) {
+            // the warp takes whole trees: its 32 pixels walk the same tree together, so the upper
+            // levels are broadcast loads and neighbouring pixels tend to leave at similar depths
+            const unsigned my = sbase + buf * tile_bytes + (unsigned)lane * 4u;
+            const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+            unsigned *cnt = reinterpret_cast<unsigned *>(smem_raw + o_cnt + buf * 128u);
+            int t = 0;
+            if (lane == 0) t = (int)atomicAdd(cnt, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            while (t < ntree) {
+                if (active) {
+                    unsigned na = SM_U32(o_root + 4u * (unsigned)t);
+                    uint2 nd = lds_node(na);
+                    while ((int)nd.y < 0) {
+                        const float xv = lds_f32(scaled_add4(nd.y & 0x1fe0u, my));
+                        na = (xv <= __uint_as_float(nd.x)) ? na + 8u : (nd.y >> 13);
+                        nd = lds_node(na);
+                    }
+                    SM_U2(lv + 256u * (unsigned)t) = nd;
+                }
+                if (lane == 0) t = (int)atomicAdd(cnt, 1u);
+                t = __shfl_sync(0xffffffffu, t, 0);
+            }
+        } else
         if (active) {
             const unsigned my = sbase + buf * tile_bytes + (unsigned)lane * 4u;
             const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
@@ -1605,6 +1629,8 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
             if (!strcmp(e, "pipe16")) cfg = 1;
             else if (!strcmp(e, "dyn32")) cfg = 2;
             else if (!strcmp(e, "dyn16")) cfg = 3;
+            else if (!strcmp(e, "wpipe32")) cfg = 4;
+            else if (!strcmp(e, "wpipe16")) cfg = 5;
         }
     }
     const int nparts = (int)part_begin.size() - 1;
@@ -1614,19 +1640,22 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
         int t0 = part_begin[p], t1 = part_begin[p + 1];
         size_t smem = forest_dyn_smem((size_t)(f->off[t1] - f->off[t0]), t1 - t0, F);
         KLaunch k(c, P_FOREST);
-#define NLF_LAUNCH_COOP(KERN, A)                                                                                    \
+#define NLF_LAUNCH_COOP(KERN, A, ...)                                                                               \
         do {                                                                                                        \
-            NLF_CUDA(cudaFuncSetAttribute(KERN<A>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+            auto kern = KERN<A, ##__VA_ARGS__>;                                                                     \
+            NLF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
                                           (int)(smem_max - 64)));                                                   \
-            KERN<A><<<c->sm_count, 32 * A, smem, c->stream>>>(                                                      \
+            kern<<<c->sm_count, 32 * A, smem, c->stream>>>(                                                         \
                 f->d_nodes2, f->d_off, t0, t1, T, F, b->d_pix, b->d_nanmask, b->d_featT, b->d_group_counter,        \
                 b->d_jobs, b->lower, w, b->ndp, acc, p == 0, p == nparts - 1);                                      \
         } while (0)
         switch (cfg) {
-            case 1: NLF_LAUNCH_COOP(k_forest_pipe, 16); break;
+            case 1: NLF_LAUNCH_COOP(k_forest_pipe, 16, false); break;
             case 2: NLF_LAUNCH_COOP(k_forest_dyn, 32); break;
             case 3: NLF_LAUNCH_COOP(k_forest_dyn, 16); break;
-            default: NLF_LAUNCH_COOP(k_forest_pipe, 32); break;
+            case 4: NLF_LAUNCH_COOP(k_forest_pipe, 32, true); break;
+            case 5: NLF_LAUNCH_COOP(k_forest_pipe, 16, true); break;
+            default: NLF_LAUNCH_COOP(k_forest_pipe, 32, false); break;
         }
 #undef NLF_LAUNCH_COOP
         NLF_CUDA(cudaGetLastError());
