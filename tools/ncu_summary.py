@@ -67,7 +67,7 @@ def main():
     kname = col["Kernel Name"]
     seen = {}
     for r in rows:
-        name = r[kname].split("(")[0]
+        name = r[kname].split("(")[0].replace("void ", "")
         seen.setdefault(name, []).append(r)
     lines = ["# " + a.title, ""]
     if a.command:
