@@ -321,7 +321,7 @@ def main():
     ms = ctx.timer_stop()
     barrier()
     wall_ms = 1000.0 * (time.perf_counter() - t0)
-    launches = ctx.launch_count() - launches0
+    launches = sum_over_ranks(float(ctx.launch_count() - launches0))      # whole job, like `value`
     mark1 = sampler.mark()
     ms = max_over_ranks(max(ms, 0.0))
     total_scored = sum_over_ranks(float(scored_per_step)) * args.steps
@@ -422,7 +422,7 @@ def main():
                        "band_cells_rank0": nband},
             "wall_ms_per_step": wall_ms / args.steps,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:                   # reported at N=1 only
             cores = os.cpu_count() or 1
             items = [(G, None, ch) for G, ch in zip(host_mats[:8], chains[:8])]
             workers = min(cores, 3 * len(items))
