@@ -314,14 +314,14 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     __shared__ double Et[TR][TC];
     __shared__ unsigned char Hs[TR][TC];
     __shared__ double Vx[S][VC];
-    __shared__ double red_min[2][S][32];      // double buffered: one block barrier per row
-    __shared__ double red_max[2][S][32];
+    __shared__ double2 red_mm[2][S][32];      // {row min, row max}, double buffered
+    __shared__ double fin_mn[2][32], fin_den[2][32], fin_rden[2][32];   // window min, max - min, 1 / (max - min)
     __shared__ unsigned passmask[TX];
     __shared__ unsigned s_rowbase[TX];       // first feature slot of every tile row
     __shared__ unsigned s_slots_ok;
     __shared__ unsigned char s_items[2 * TX];
     __shared__ int s_nitems;
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_bar[2], s_fin[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- tile -> (job, x0, d0)
@@ -418,8 +418,11 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
     }
 
     // ---- phase 2: rows.  Work items = (tile row, O/E or raw source) that have at least one window.
-    // Per item: axis-1 pass -> row min/max to shared memory -> mbarrier ARRIVE -> axis-0 pass of the
-    // NEXT item (independent work that hides the barrier latency) -> mbarrier WAIT -> normalise, store.
+    // Per item: axis-1 pass -> row min/max to shared memory -> mbarrier ARRIVE (s_bar) -> axis-0 pass of
+    // the NEXT item (independent work that hides the barrier latency) -> mbarrier WAIT (s_fin) -> normalise,
+    // store.  Between the two barriers ONE warp (round robin over the items) folds the 2W+1 row extrema
+    // of every window into min, max - min and its reciprocal and publishes them, so the other warps
+    // do not repeat that reduction and division.
     if (tid == 0) {
         int k = 0;
         for (int xi = 0; xi < TX; xi++) {
@@ -430,6 +433,8 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
         s_nitems = k;
         mbar_init(&s_bar[0], NT);
         mbar_init(&s_bar[1], NT);
+        mbar_init(&s_fin[0], 32);
+        mbar_init(&s_fin[1], 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -489,30 +494,39 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
             else { rmin = (v < rmin) ? v : rmin; rmax = (v > rmax) ? v : rmax; }
         }
         if (has_nan) { rmin = qnan; rmax = qnan; }
-        red_min[rb][warp][lane] = rmin;
-        red_max[rb][warp][lane] = rmax;
+        red_mm[rb][warp][lane] = make_double2(rmin, rmax);
         mbar_arrive(&s_bar[rb]);                       // release: my row's min/max are published
-        if (it + 1 < nitems) stage_a(s_items[it + 1]);
-        mbar_wait(&s_bar[rb], (it >> 1) & 1u);         // acquire: all window rows are in
-        double mn = red_min[rb][0][lane], mx = red_max[rb][0][lane];
-        bool nn = (mn != mn);
+        const unsigned par = (it >> 1) & 1u;
+        if (warp == it % S) {
+            mbar_wait(&s_bar[rb], par);                // acquire: all window rows are in
+            double2 m0 = red_mm[rb][0][lane];
+            double mn = m0.x, mx = m0.y;
+            bool nn = (mn != mn);
 #pragma unroll
-        for (int a = 1; a < S; a++) {
-            double u = red_min[rb][a][lane], v = red_max[rb][a][lane];
-            nn |= (u != u);
-            mn = (u < mn) ? u : mn;
-            mx = (v > mx) ? v : mx;
+            for (int a = 1; a < S; a++) {
+                const double2 m = red_mm[rb][a][lane];
+                nn |= (m.x != m.x);
+                mn = (m.x < mn) ? m.x : mn;
+                mx = (m.y > mx) ? m.y : mx;
+            }
+            if (nn) { mn = qnan; mx = qnan; }
+            const double den = __dsub_rn(mx, mn);
+            const bool fast_ok = (den > 1e-290) && (den < 1e300);
+            fin_mn[rb][lane] = mn;
+            fin_den[rb][lane] = den;
+            fin_rden[rb][lane] = fast_ok ? __ddiv_rn(1.0, den) : 0.0;    // 0 marks "always divide"
+            mbar_arrive(&s_fin[rb]);
         }
-        if (nn) { mn = qnan; mx = qnan; }
+        if (it + 1 < nitems) stage_a(s_items[it + 1]);
+        mbar_wait(&s_fin[rb], par);                    // acquire: the window extrema are published
         if ((mm >> lane) & 1u) {
             bool f_nan = false;
-            const double den = __dsub_rn(mx, mn);
+            const double mn = fin_mn[rb][lane], den = fin_den[rb][lane], rden = fin_rden[rb][lane];
             // float32(fl64(num/den)) without 13 fp64 divisions: p = fl64(num * fl64(1/den)) is within
             // 2.01 ulp64 of the exact quotient, so it rounds to the same float32 unless it sits within
             // 8 ulp64 of a float32 rounding boundary (low 29 mantissa bits ~ 0x10000000) or in the
             // float32 subnormal range; those (about 1 in 3e7) take the exact division.
-            const bool fast_ok = (den > 1e-290) && (den < 1e300);
-            const double rden = __ddiv_rn(1.0, fast_ok ? den : 1.0);
+            const bool fast_ok = (rden != 0.0);
 #pragma unroll
             for (int b = 0; b < S; b++) {
                 const double num = __dsub_rn(out[b], mn);
