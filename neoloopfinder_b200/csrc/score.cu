@@ -524,18 +524,31 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
             const double mn = fin_mn[rb][lane], den = fin_den[rb][lane], rden = fin_rden[rb][lane];
             // float32(fl64(num/den)) without 13 fp64 divisions: p = fl64(num * fl64(1/den)) is within
             // 2.01 ulp64 of the exact quotient, so it rounds to the same float32 unless it sits within
-            // 8 ulp64 of a float32 rounding boundary (low 29 mantissa bits ~ 0x10000000) or in the
-            // float32 subnormal range; those (about 1 in 3e7) take the exact division.
-            const bool fast_ok = (rden != 0.0);
+            // 8 ulp64 of a float32 rounding boundary (low 29 mantissa bits ~ 0x10000000) or below the
+            // float32 normal range (p < 2^-125, p != 0 up to doubles that round to 0 anyway); rows with
+            // such a value (about 1 cell in 3e7) are redone with the exact division.  In this branch den
+            // is finite and positive, so every value is finite, non-negative and no NaN can appear.
+            if (rden != 0.0) {
+                bool risky = false;
 #pragma unroll
-            for (int b = 0; b < S; b++) {
-                const double num = __dsub_rn(out[b], mn);
-                double f = __dmul_rn(num, rden);
-                const unsigned dropped = (unsigned)__double2loint(f) & 0x1fffffffu;
-                const bool risky = !fast_ok || (dropped - 0x0ffffff8u <= 16u) || (f < 1.2e-38 && f != 0.0);
-                if (risky) f = __ddiv_rn(num, den);
-                f_nan |= (f != f);
-                fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(f);
+                for (int b = 0; b < S; b++) {
+                    const double f = __dmul_rn(__dsub_rn(out[b], mn), rden);
+                    const unsigned flo = (unsigned)__double2loint(f), fhi = (unsigned)__double2hiint(f);
+                    risky |= ((flo & 0x1fffffffu) - 0x0ffffff8u <= 16u) | (fhi - 1u < 0x381fffffu);
+                    fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(f);
+                }
+                if (risky) {
+#pragma unroll
+                    for (int b = 0; b < S; b++)
+                        fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(__ddiv_rn(__dsub_rn(out[b], mn), den));
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < S; b++) {
+                    const double f = __ddiv_rn(__dsub_rn(out[b], mn), den);
+                    f_nan |= (f != f);
+                    fdst[(size_t)(warp * S + b) * 32] = __double2float_rn(f);
+                }
             }
             // windows with NaN features (constant window, or a zero in the expected table) take the
             // general forest kernel, which implements sklearn's missing_go_to_left routing
