@@ -109,42 +109,116 @@ struct nlf_ctx {
     // its single stream, so a buffer handed back here can be reused by the next request at once;
     // steady-state steps then make no driver allocation at all (cudaMalloc of multi-GB feature
     // buffers costs tens of ms to seconds and showed up as latency spikes in the end-to-end path).
-    struct Big { void *p; size_t bytes; bool busy; };
+    struct Big { void *p; size_t bytes; bool busy; cudaEvent_t freed; };
     std::vector<Big> bigs;
-    cudaError_t big_alloc(void **out, size_t bytes)
+    // `consumer`: the stream that will touch the buffer first.  Buffers are handed back in
+    // main-stream order (big_free records an event there); another stream waits for that event.
+    cudaError_t big_alloc(void **out, size_t bytes, cudaStream_t consumer = nullptr)
     {
         int best = -1;
         for (int i = 0; i < (int)bigs.size(); i++)
             if (!bigs[i].busy && bigs[i].bytes >= bytes && bigs[i].bytes <= bytes + bytes / 4 + (1 << 20) &&
                 (best < 0 || bigs[i].bytes < bigs[best].bytes))
                 best = i;
-        if (best >= 0) { bigs[best].busy = true; *out = bigs[best].p; return cudaSuccess; }
+        if (best >= 0) {
+            bigs[best].busy = true;
+            *out = bigs[best].p;
+            if (consumer && consumer != stream && bigs[best].freed) return cudaStreamWaitEvent(consumer, bigs[best].freed, 0);
+            return cudaSuccess;
+        }
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
             // release idle cached buffers and retry once
             cudaGetLastError();
             cudaStreamSynchronize(stream);
-            for (auto &b : bigs) if (!b.busy && b.p) { cudaFree(b.p); b.p = nullptr; }
+            for (auto &b : bigs) if (!b.busy && b.p) { cudaFree(b.p); b.p = nullptr; if (b.freed) cudaEventDestroy(b.freed); }
             std::vector<Big> keep;
             for (auto &b : bigs) if (b.p) keep.push_back(b);
             bigs.swap(keep);
             e = cudaMalloc(&p, bytes);
             if (e != cudaSuccess) return e;
         }
-        bigs.push_back({p, bytes, true});
+        bigs.push_back({p, bytes, true, nullptr});
         *out = p;
         return cudaSuccess;
     }
     void big_free(void *p)
     {
         if (!p) return;
-        for (auto &b : bigs) if (b.p == p) { b.busy = false; return; }
+        for (auto &b : bigs)
+            if (b.p == p) {
+                b.busy = false;
+                if (!b.freed) cudaEventCreateWithFlags(&b.freed, cudaEventDisableTiming);
+                if (b.freed) cudaEventRecord(b.freed, stream);
+                return;
+            }
     }
     void big_release_all()
     {
-        for (auto &b : bigs) if (b.p) cudaFree(b.p);
+        for (auto &b : bigs) { if (b.p) cudaFree(b.p); if (b.freed) cudaEventDestroy(b.freed); }
         bigs.clear();
+    }
+
+    // Host -> device uploads of job inputs run on a second stream (copy + the small kernel that
+    // turns the upload into the resident band), through a ring of staging buffers, so the inputs
+    // of the next job -- or of the next sub-batch -- arrive while kernels of earlier work occupy the
+    // main stream.  The batch records an event after its last input; the main stream waits for it
+    // before the first kernel that reads the bands.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t fence = nullptr;
+    struct Stage { void *p = nullptr; size_t bytes = 0; cudaEvent_t used = nullptr; bool pending = false; };
+    static constexpr int NSTAGE = 3;
+    Stage stages[NSTAGE];
+    int stage_next = 0;
+    // order the copy stream after everything enqueued on the main stream so far
+    cudaError_t copy_fence()
+    {
+        cudaError_t e;
+        if (!fence && (e = cudaEventCreateWithFlags(&fence, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(fence, stream)) != cudaSuccess) return e;
+        return cudaStreamWaitEvent(copy_stream, fence, 0);
+    }
+    // a staging buffer of at least `bytes`, safe to overwrite from the copy stream
+    cudaError_t stage_acquire(size_t bytes, void **dev)
+    {
+        Stage &s = stages[stage_next];
+        stage_next = (stage_next + 1) % NSTAGE;
+        cudaError_t e;
+        if (!s.used && (e = cudaEventCreateWithFlags(&s.used, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if (s.bytes < bytes) {
+            if (s.pending) cudaEventSynchronize(s.used);
+            s.pending = false;
+            if (s.p) cudaFree(s.p);
+            s.p = nullptr;
+            s.bytes = 0;
+            const size_t want = bytes + bytes / 4;
+            if (cudaMalloc(&s.p, want) != cudaSuccess) {
+                cudaGetLastError();
+                if ((e = cudaMalloc(&s.p, bytes)) != cudaSuccess) return e;
+                s.bytes = bytes;
+            } else {
+                s.bytes = want;
+            }
+        }
+        // same stream as the previous user of the buffer: stream order is enough
+        *dev = s.p;
+        return cudaSuccess;
+    }
+    void stage_release(void *dev)
+    {
+        for (auto &s : stages)
+            if (s.p == dev) { cudaEventRecord(s.used, copy_stream); s.pending = true; return; }
+    }
+    void stage_release_all()
+    {
+        for (auto &s : stages) {
+            if (s.p) cudaFree(s.p);
+            if (s.used) cudaEventDestroy(s.used);
+            s = Stage();
+        }
+        if (fence) cudaEventDestroy(fence);
+        fence = nullptr;
     }
 
     cudaEvent_t get_event()
@@ -154,19 +228,19 @@ struct nlf_ctx {
         cudaEventCreate(&e);
         return e;
     }
-    void prof_begin(int cls, cudaEvent_t *a)
+    void prof_begin(int cls, cudaEvent_t *a, cudaStream_t s)
     {
         launches++;
         if (!profile) return;
         *a = get_event();
-        cudaEventRecord(*a, stream);
+        cudaEventRecord(*a, s);
         (void)cls;
     }
-    void prof_end(int cls, cudaEvent_t a)
+    void prof_end(int cls, cudaEvent_t a, cudaStream_t s)
     {
         if (!profile) return;
         cudaEvent_t b = get_event();
-        cudaEventRecord(b, stream);
+        cudaEventRecord(b, s);
         recs.push_back({cls, a, b});
     }
     void prof_resolve()
@@ -186,9 +260,9 @@ struct nlf_ctx {
 
 // RAII-free helper: launch bracket used as  { KLaunch k(ctx, cls); kernel<<<...>>>(...); }
 struct KLaunch {
-    nlf_ctx *c; int cls; cudaEvent_t a = nullptr;
-    KLaunch(nlf_ctx *ctx, int cls_) : c(ctx), cls(cls_) { c->prof_begin(cls, &a); }
-    ~KLaunch() { c->prof_end(cls, a); }
+    nlf_ctx *c; int cls; cudaEvent_t a = nullptr; cudaStream_t s;
+    KLaunch(nlf_ctx *ctx, int cls_, cudaStream_t st = nullptr) : c(ctx), cls(cls_), s(st ? st : ctx->stream) { c->prof_begin(cls, &a, s); }
+    ~KLaunch() { c->prof_end(cls, a, s); }
 };
 
 // ---------------------------------------------------------------------------------------------

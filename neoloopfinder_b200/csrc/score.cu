@@ -1242,6 +1242,8 @@ struct nlf_batch {
     int W = 0, ndp = 0, ndt = 0;
     bool keep_slots = false;
     std::vector<HostJob> jobs;
+    cudaEvent_t ev_inputs = nullptr;         // recorded on the copy stream after the last uploaded input
+    bool inputs_pending = false;
     // pools: one allocation per batch instead of a dozen per job
     int *d_status = nullptr;                 // [NLF_MAX_JOBS]
     unsigned long long *d_counts = nullptr;  // [NLF_MAX_JOBS*4 + 1]; the last word counts the Donuts
@@ -1302,6 +1304,7 @@ NLF_EXPORT int nlf_ctx_create(int device, nlf_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     NLF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    NLF_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     NLF_CUDA(cudaEventCreate(&c->t0));
     NLF_CUDA(cudaEventCreate(&c->t1));
     cudaMemPool_t pool;
@@ -1316,12 +1319,15 @@ NLF_EXPORT int nlf_ctx_destroy(nlf_ctx *c)
 {
     if (!c) return NLF_OK;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->stream);
     c->prof_resolve();
     c->big_release_all();
+    c->stage_release_all();
     for (auto e : c->free_events) cudaEventDestroy(e);
     cudaEventDestroy(c->t0);
     cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
     return NLF_OK;
@@ -1330,6 +1336,7 @@ NLF_EXPORT int nlf_ctx_destroy(nlf_ctx *c)
 NLF_EXPORT int nlf_ctx_sync(nlf_ctx *c)
 {
     NLF_CUDA(cudaSetDevice(c->device));
+    NLF_CUDA(cudaStreamSynchronize(c->copy_stream));
     NLF_CUDA(cudaStreamSynchronize(c->stream));
     return NLF_OK;
 }
@@ -1338,6 +1345,7 @@ NLF_EXPORT int nlf_timer_start(nlf_ctx *c)
 {
     NLF_CUDA(cudaSetDevice(c->device));
     NLF_CUDA(cudaEventRecord(c->t0, c->stream));
+    NLF_CUDA(cudaStreamWaitEvent(c->copy_stream, c->t0, 0));     // uploads of the timed region start after t0
     return NLF_OK;
 }
 
@@ -1504,8 +1512,25 @@ NLF_EXPORT int nlf_batch_create(nlf_ctx *ctx, int lower, int upper, nlf_batch **
     NLF_CUDA(cudaMallocAsync(&b->d_counts, sizeof(unsigned long long) * (NLF_MAX_JOBS * 4 + 1), s));
     NLF_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * NLF_MAX_JOBS, s));
     NLF_CUDA(cudaMemsetAsync(b->d_counts, 0, sizeof(unsigned long long) * (NLF_MAX_JOBS * 4 + 1), s));
+    NLF_CUDA(ctx->copy_fence());                    // inputs of this batch come after everything enqueued so far
     *out = b;
     return NLF_OK;
+}
+
+// inputs arrive on the copy stream: remember the point the main stream has to wait for
+static cudaError_t inputs_uploaded(nlf_batch *b)
+{
+    cudaError_t e;
+    if (!b->ev_inputs && (e = cudaEventCreateWithFlags(&b->ev_inputs, cudaEventDisableTiming)) != cudaSuccess) return e;
+    b->inputs_pending = true;
+    return cudaEventRecord(b->ev_inputs, b->ctx->copy_stream);
+}
+
+static cudaError_t wait_inputs(nlf_batch *b)
+{
+    if (!b->inputs_pending) return cudaSuccess;
+    b->inputs_pending = false;
+    return cudaStreamWaitEvent(b->ctx->stream, b->ev_inputs, 0);
 }
 
 static int check_can_add(nlf_batch *b)
@@ -1526,16 +1551,31 @@ NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
     HostJob j;
     j.n = n;
     double *d_dense;
-    NLF_CUDA(c->big_alloc((void **)&d_dense, sizeof(double) * (size_t)n * n));
-    NLF_CUDA(c->big_alloc((void **)&j.d_band, sizeof(double) * (size_t)n * b->pitch));
-    NLF_CUDA(cudaMemcpyAsync(d_dense, G, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+    cudaStream_t cs = c->copy_stream;
+    NLF_CUDA(c->big_alloc((void **)&j.d_band, sizeof(double) * (size_t)n * b->pitch, cs));
+    NLF_CUDA(c->stage_acquire(sizeof(double) * (size_t)n * n, (void **)&d_dense));
+    if (n < 1024) {
+        NLF_CUDA(cudaMemcpyAsync(d_dense, G, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, cs));
+    } else {
+        // only the cells k_bandify reads (13 sub-diagonals and bw super-diagonals) cross the bus: row
+        // blocks of 128 rows, each a 2-D copy of the columns its rows can touch
+        const int RB = 128;
+        for (int r0 = 0; r0 < n; r0 += RB) {
+            const int r1 = std::min(n, r0 + RB);
+            const int c0 = std::max(0, r0 - 13), c1 = std::min(n, r1 - 1 + b->bw);
+            NLF_CUDA(cudaMemcpy2DAsync(d_dense + (size_t)r0 * n + c0, sizeof(double) * (size_t)n, G + (size_t)r0 * n + c0,
+                                       sizeof(double) * (size_t)n, sizeof(double) * (size_t)(c1 - c0), (size_t)(r1 - r0),
+                                       cudaMemcpyHostToDevice, cs));
+        }
+    }
     {
-        KLaunch k(c, P_BANDIFY);
+        KLaunch k(c, P_BANDIFY, cs);
         dim3 grid((b->pitch + 127) / 128, n);
-        k_bandify<<<grid, 128, 0, c->stream>>>(d_dense, n, b->bw, b->pitch, j.d_band, b->d_status + b->jobs.size());
+        k_bandify<<<grid, 128, 0, cs>>>(d_dense, n, b->bw, b->pitch, j.d_band, b->d_status + b->jobs.size());
     }
     NLF_CUDA(cudaGetLastError());
-    c->big_free(d_dense);
+    c->stage_release(d_dense);
+    NLF_CUDA(inputs_uploaded(b));
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
 }
@@ -1551,16 +1591,18 @@ NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int p
     HostJob j;
     j.n = n;
     double *d_src;
-    NLF_CUDA(c->big_alloc((void **)&d_src, sizeof(double) * (size_t)n * pitch));
-    NLF_CUDA(c->big_alloc((void **)&j.d_band, sizeof(double) * (size_t)n * b->pitch));
-    NLF_CUDA(cudaMemcpyAsync(d_src, band, sizeof(double) * (size_t)n * pitch, cudaMemcpyHostToDevice, c->stream));
+    cudaStream_t cs = c->copy_stream;
+    NLF_CUDA(c->big_alloc((void **)&j.d_band, sizeof(double) * (size_t)n * b->pitch, cs));
+    NLF_CUDA(c->stage_acquire(sizeof(double) * (size_t)n * pitch, (void **)&d_src));
+    NLF_CUDA(cudaMemcpyAsync(d_src, band, sizeof(double) * (size_t)n * pitch, cudaMemcpyHostToDevice, cs));
     {
-        KLaunch k(c, P_BANDIFY);
+        KLaunch k(c, P_BANDIFY, cs);
         dim3 grid((b->pitch + 127) / 128, n);
-        k_band_copy<<<grid, 128, 0, c->stream>>>(d_src, n, pitch, b->bw, b->pitch, j.d_band);
+        k_band_copy<<<grid, 128, 0, cs>>>(d_src, n, pitch, b->bw, b->pitch, j.d_band);
     }
     NLF_CUDA(cudaGetLastError());
-    c->big_free(d_src);
+    c->stage_release(d_src);
+    NLF_CUDA(inputs_uploaded(b));
     b->jobs.push_back(j);
     return (int)b->jobs.size() - 1;
 }
@@ -1747,6 +1789,7 @@ static int upload_jobs(nlf_batch *b, int w)
 // K5: diagonal means, isotonic expected, candidate count.  Independent of the model.
 static int batch_prepare(nlf_batch *b)
 {
+    NLF_CUDA(wait_inputs(b));
     if (b->prepared) return NLF_OK;
     nlf_ctx *c = b->ctx;
     const int nj = (int)b->jobs.size();
@@ -2119,6 +2162,7 @@ NLF_EXPORT int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const i
     if (inside < 2) return NLF_OK;
     for (long long k = 0; k < nc; k++)
         if (xi[k] < 0 || yi[k] < 0 || xi[k] >= J.n || yi[k] >= J.n) return fail(NLF_ERR_ARG, "coordinate %lld out of range", k);
+    NLF_CUDA(wait_inputs(b));
     int *d_x, *d_y;
     unsigned char *d_pass;
     double *d_fea, *d_exp;
@@ -2196,6 +2240,7 @@ NLF_EXPORT int nlf_batch_reset(nlf_batch *b)
     NLF_CUDA(cudaMemsetAsync(b->d_counts + (size_t)NLF_MAX_JOBS * 4, 0, sizeof(unsigned long long), c->stream));
     b->prepared = b->scored = b->counted = false;
     b->donuts_cached = false;
+    NLF_CUDA(c->copy_fence());                      // later inputs come after the resets above
     return NLF_OK;
 }
 
@@ -2261,6 +2306,8 @@ NLF_EXPORT int nlf_batch_destroy(nlf_batch *b)
     nlf_ctx *c = b->ctx;
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
+    wait_inputs(b);                                 // uploads in flight finish before their buffers are handed back
+    if (b->ev_inputs) cudaEventDestroy(b->ev_inputs);
     free_score_outputs(b);
     for (auto &j : b->jobs)
         if (j.d_band) {

@@ -5,6 +5,8 @@ Thin, typed wrappers over include/nlf_b200.h; the reference-shaped classes in ``
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -324,19 +326,24 @@ def local_clustering_gpu(ij, val, res, min_count=2, r=15000, chain_i=None, chain
     return out
 
 
-def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, min_count: int = 2,
-                   chains: Optional[Sequence] = None, no_pool: bool = False, r: int = 15000):
-    """The scoring path for a whole batch: candidates -> features -> forest -> threshold ->
-    pooling (callers.py:614-639 for every matrix of the batch).
-
-    chains[job] = per-gap-free-bin block id (``chains[index_map[i]]`` of the reference) or None.
-    Returns (loops, counts): loops[job] = (i, j, prob) arrays of the called loops, counts =
-    (n_candidates, n_scored, n_donuts) arrays.
-    """
-    batch.score(forest, exp_arr, thre, forest.w)
-    n_cand, n_scored, n_don = batch.counts()
-    dj_, di, dj, dp, dv = batch.donuts_all()
-    nj = batch.njobs
+def _pool_scored(batches: Sequence[ScoreBatch], thre: float, res: int, min_count: int, chains: Optional[Sequence],
+                 no_pool: bool, r: int):
+    """Threshold results of one or more scored batches -> pooled loops, with ONE pooling pass over
+    the Donuts of all of them (jobs are numbered consecutively across the batches)."""
+    cand, scored, don, parts = [], [], [], []
+    base = 0
+    for batch in batches:
+        n_cand, n_scored, n_don = batch.counts()
+        dj_, di, dj, dp, dv = batch.donuts_all()
+        cand.append(n_cand); scored.append(n_scored); don.append(n_don)
+        parts.append((dj_.astype(np.int64) + base, di, dj, dp, dv))
+        base += batch.njobs
+    nj = base
+    n_cand, n_scored, n_don = (np.concatenate(x) if len(x) > 1 else x[0] for x in (cand, scored, don))
+    if len(parts) > 1:
+        dj_, di, dj, dp, dv = (np.concatenate([p[k] for p in parts]) for k in range(5))
+    else:
+        dj_, di, dj, dp, dv = parts[0]
     empty = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64))
     # callers.py:619-620: fewer than two scored windows -> no call at all for that matrix
     if len(dj_):
@@ -366,7 +373,7 @@ def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, mi
         ks = key[order]
         starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
         off = np.r_[starts, len(ks)].astype(np.int64)
-        keep_sorted = pool_flat(off, di[order], dj[order], dv[order], res, min_count, r, batch.ctx)
+        keep_sorted = pool_flat(off, di[order], dj[order], dv[order], res, min_count, r, batches[0].ctx)
         keep = np.empty(len(dj_), dtype=bool)
         keep[order] = keep_sorted
     loops = [empty] * nj
@@ -381,14 +388,47 @@ def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, mi
     return loops, (n_cand, n_scored, n_don)
 
 
+def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, min_count: int = 2,
+                   chains: Optional[Sequence] = None, no_pool: bool = False, r: int = 15000):
+    """The scoring path for a whole batch: candidates -> features -> forest -> threshold ->
+    pooling (callers.py:614-639 for every matrix of the batch).
+
+    chains[job] = per-gap-free-bin block id (``chains[index_map[i]]`` of the reference) or None.
+    Returns (loops, counts): loops[job] = (i, j, prob) arrays of the called loops, counts =
+    (n_candidates, n_scored, n_donuts) arrays.
+    """
+    batch.score(forest, exp_arr, thre, forest.w)
+    return _pool_scored([batch], thre, res, min_count, chains, no_pool, r)
+
+
+PIPELINE_MIN_JOBS = 8       # matrices per sub-batch below which splitting a batch stops paying
+PIPELINE_DEPTH = 4          # sub-batches of one score_matrices call
+
+
 def score_matrices(mats: Sequence[np.ndarray], forest, exp_arr, thre: float, res: int, min_count: int = 2,
-                   chains: Optional[Sequence] = None, no_pool: bool = False, upper: int = 400, ctx=None):
-    """Host gap-free matrices in -> called loops out, one batch on one GPU (the end-to-end call
-    ``bench.py`` times: host->device copies, every kernel, device->host results)."""
-    batch = ScoreBatch(4, upper, ctx)
+                   chains: Optional[Sequence] = None, no_pool: bool = False, upper: int = 400, ctx=None,
+                   depth: Optional[int] = None):
+    """Host gap-free matrices in -> called loops out on one GPU (the end-to-end call ``bench.py``
+    times: host->device copies, every kernel, device->host results).
+
+    The matrices are cut into up to ``depth`` sub-batches.  Uploads run on the context's copy
+    stream, scoring on its main stream, and nothing here waits for the device until every
+    sub-batch is enqueued: the upload of sub-batch k+1 overlaps the kernels of sub-batch k.
+    Results are independent per matrix, so the split does not change them."""
+    mats = list(mats)
+    nj = len(mats)
+    if depth is None:
+        depth = int(os.environ.get("NLF_PIPELINE_DEPTH", PIPELINE_DEPTH))
+    depth = max(1, min(depth, nj // PIPELINE_MIN_JOBS))
+    cuts = [nj * k // depth for k in range(depth + 1)]
+    # every sub-batch object first: creating one orders the copy stream after the main stream
+    batches = [ScoreBatch(4, upper, ctx) for _ in range(depth)]
     try:
-        for G in mats:
-            batch.add_dense(G)
-        return score_and_pool(batch, forest, exp_arr, thre, res, min_count, chains, no_pool)
+        for b, lo, hi in zip(batches, cuts[:-1], cuts[1:]):
+            for G in mats[lo:hi]:
+                b.add_dense(G)
+            b.score(forest, exp_arr, thre, forest.w)
+        return _pool_scored(batches, thre, res, min_count, chains, no_pool, 15000)
     finally:
-        batch.close()
+        for b in batches:
+            b.close()

@@ -262,10 +262,33 @@ def test_long_banded_chromosome_matches_oracle():
         b.close()
     finally:
         del os.environ["NLF_FEATURE_BUDGET_MB"]
-    cl, pr, _ = co.score_matrix(G, exp_arr, co.sklearn_forest_arrays(joblib.load(model_path)), 6)
+    cl, pr, fea32 = co.score_matrix(G, exp_arr, co.sklearn_forest_arrays(joblib.load(model_path)), 6)
     assert len(pr) > 500000
     assert np.array_equal(np.stack([i, j], 1), cl)
     assert np.array_equal(p, pr)
+    # the float32 features themselves, bit for bit (8.5e7 cells: a handful of them fall next to a
+    # float32 rounding boundary and take the kernel's exact-division path)
+    # ... fed as the dense matrix this time: above 1024 bins only the cells near the band are uploaded
+    b = ScoreBatch(4, 400, ctx)
+    b.keep_features(True)
+    b.add_dense(G)
+    b.score(forest, exp_arr, 0.9)
+    got = b.features32(0)
+    i2, j2, p2 = b.scored(0)
+    b.close()
+    assert got.shape == fea32.shape
+    assert np.array_equal(got.view(np.uint32), fea32.view(np.uint32))
+    assert np.array_equal(np.stack([i2, j2], 1), cl) and np.array_equal(p2, pr)
+    # a non-zero cell below the diagonal is reported, not mis-scored (the trimmed upload still covers
+    # the 13 sub-diagonals Peakachu keeps)
+    bad = G.copy()
+    bad[1500, 1490] = 3.0
+    b = ScoreBatch(4, 400, ctx)
+    b.add_dense(bad)
+    b.score(forest, exp_arr, 0.9)
+    with pytest.raises(_lib.NLFError):
+        b.scored(0)
+    b.close()
 
 
 def test_calculate_expected_gpu_equals_port():

@@ -1,0 +1,26 @@
+"""Host-side timeline of the pipelined end-to-end call (tuning helper, run under gpurun):
+when each add / score / result phase of every sub-batch returns, for several pipeline depths."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from neoloopfinder_b200 import _lib
+from neoloopfinder_b200.forest import load_forest
+from neoloopfinder_b200.scoring import ScoreBatch, score_and_pool, score_matrices
+
+ctx = _lib.Context.get(0)
+forest = load_forest(bench.MODEL, ctx)
+clr, lines, expected = bench.build_assemblies(0, 50)
+exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
+mats, chains = bench.gap_free_matrices_gpu(clr, lines, expected, ctx)
+pinned = [torch.from_numpy(G).pin_memory() for G in mats]
+host = [t.numpy() for t in pinned]
+for depth in (1, 2, 3, 4, 6):
+    for rep in range(4):
+        ctx.l2_flush(); ctx.sync()
+        t0 = time.perf_counter()
+        score_matrices(host, forest, exp_arr, 0.9, 10000, 2, chains, False, 400, ctx, depth=depth)
+        ctx.sync()
+        dt = 1e3 * (time.perf_counter() - t0)
+    print("depth %d: e2e step %.2f ms" % (depth, dt))
