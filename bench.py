@@ -398,7 +398,7 @@ def main():
             "algorithmic_ops_per_pixel": 4940,
         }
         forest_info = {
-            "kernel": "k_forest_pipe<32> x parts + k_forest_nan", "ms_per_step": forest_ms,
+            "kernel": "k_forest_pipe<32 warps, 2 trees per lane> x parts + k_forest_nan", "ms_per_step": forest_ms,
             "node_visits_per_s": 1617.0 * scored_per_step / (forest_ms * 1e-3) if forest_ms else None,
             "note": "about 1617 node visits per pixel (100 trees, mean leaf depth 16.2); bound by shared-memory "
                     "wavefronts and issue slots, see profiles/r01_ncu_summary.md",

@@ -783,7 +783,7 @@ __device__ __forceinline__ float lds_f32(unsigned addr)
 // next tile at once; the tile's summing warp (round robin) waits for `done`, adds the leaf values
 // in tree order, resets the tree counters and only then issues the TMA copy that refills the
 // buffer two tiles later -- which is also what protects leafv/cnt from early reuse.
-template <int NW, bool WARP_GRAB>
+template <int NW, bool WARP_GRAB, int ILP = 1>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off, int t0, int t1, int T_total, int F,
               const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask, const float *__restrict__ featT,
@@ -810,7 +810,7 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
     // offset) and (y & 0x1fe0) << 2 is the byte offset of the feature row in the tile.
     const unsigned sbase = smem_u32(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k <= ntree; k += blockDim.x)
+    for (int k = tid; k < ntree + 8; k += blockDim.x)
         SM_U32(o_root + 4u * k) = (unsigned)((k < ntree) ? tree_off[t0 + k] - part_base : part_nodes);
     if (tid < 64) SM_U32(o_cnt + 4u * tid) = 0u;
     __syncthreads();
@@ -833,7 +833,7 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    for (int k = tid; k <= ntree; k += blockDim.x) SM_U32(o_root + 4u * k) = 0x40000u + sbase + o_nodes + 8u * SM_U32(o_root + 4u * k);
+    for (int k = tid; k < ntree + 8; k += blockDim.x) SM_U32(o_root + 4u * k) = 0x40000u + sbase + o_nodes + 8u * SM_U32(o_root + 4u * k);
     __syncthreads();
     const unsigned nslots = *slot_counter;
     const unsigned ngroups = (nslots + 31u) >> 5;
@@ -880,6 +880,41 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
                 }
                 if (lane == 0) t = (int)atomicAdd(cnt, 1u);
                 t = __shfl_sync(0xffffffffu, t, 0);
+            }
+        } else if (ILP > 1) {
+            // ILP trees per lane in flight: that many independent shared-memory load chains per warp
+            if (active) {
+                const unsigned my = sbase + buf * tile_bytes + (unsigned)lane * 4u;
+                const unsigned lv = o_leafv + buf * leafv_bytes + (unsigned)lane * 8u;
+                unsigned *cnt = reinterpret_cast<unsigned *>(smem_raw + o_cnt + buf * 128u + (unsigned)lane * 4u);
+                int t = (int)atomicAdd(cnt, (unsigned)ILP);
+                while (t < ntree) {
+                    // root table entries [ntree, ntree + 8) point at the all-zero sentinel leaf behind the part
+                    unsigned na[ILP];
+                    uint2 nd[ILP];
+#pragma unroll
+                    for (int c = 0; c < ILP; c++) na[c] = SM_U32(o_root + 4u * (unsigned)(t + c));
+#pragma unroll
+                    for (int c = 0; c < ILP; c++) nd[c] = lds_node(na[c]);
+                    while (true) {
+                        unsigned any = nd[0].y;
+#pragma unroll
+                        for (int c = 1; c < ILP; c++) any |= nd[c].y;
+                        if ((int)any >= 0) break;
+#pragma unroll
+                        for (int c = 0; c < ILP; c++) {
+                            if ((int)nd[c].y < 0) {
+                                const float xv = lds_f32(scaled_add4(nd[c].y & 0x1fe0u, my));
+                                na[c] = (xv <= __uint_as_float(nd[c].x)) ? na[c] + 8u : (nd[c].y >> 13);
+                                nd[c] = lds_node(na[c]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < ILP; c++)
+                        if (t + c < ntree) SM_U2(lv + 256u * (unsigned)(t + c)) = nd[c];
+                    t = (int)atomicAdd(cnt, (unsigned)ILP);
+                }
             }
         } else
         if (active) {
@@ -1639,7 +1674,7 @@ static int launch_features(nlf_batch *b, int tile_offset, int n_tiles, int nexp)
 static inline size_t forest_dyn_smem(size_t nodes, int ntree, int F)
 {
     return 2 * (size_t)F * 128 + 2 * (size_t)ntree * 256 + 256 + ((nodes + 2) & ~(size_t)1) * 8 +
-           sizeof(int) * (size_t)((ntree + 1 + 3) & ~3) + 64;
+           sizeof(int) * (size_t)((ntree + 8 + 3) & ~3) + 64;
 }
 
 // K8 launch: shared-memory forest parts when they fit, else the global-memory kernel.
@@ -1692,7 +1727,8 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
     }
     static int cfg = -1;
     if (cfg < 0) {
-        const char *e = getenv("NLF_FOREST_CFG");              // tuning knob: pipe32 (default), pipe16, dyn32, dyn16
+        const char *e = getenv("NLF_FOREST_CFG");              // tuning knob: default pipe32 with 2 trees per lane in flight;
+                                                               // pipe32x1, pipe32x3, pipe16, wpipe32, wpipe16, dyn32, dyn16
         cfg = 0;
         if (e) {
             if (!strcmp(e, "pipe16")) cfg = 1;
@@ -1700,6 +1736,8 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
             else if (!strcmp(e, "dyn16")) cfg = 3;
             else if (!strcmp(e, "wpipe32")) cfg = 4;
             else if (!strcmp(e, "wpipe16")) cfg = 5;
+            else if (!strcmp(e, "pipe32x1")) cfg = 6;
+            else if (!strcmp(e, "pipe32x3")) cfg = 7;
         }
     }
     const int nparts = (int)part_begin.size() - 1;
@@ -1724,7 +1762,9 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
             case 3: NLF_LAUNCH_COOP(k_forest_dyn, 16); break;
             case 4: NLF_LAUNCH_COOP(k_forest_pipe, 32, true); break;
             case 5: NLF_LAUNCH_COOP(k_forest_pipe, 16, true); break;
-            default: NLF_LAUNCH_COOP(k_forest_pipe, 32, false); break;
+            case 6: NLF_LAUNCH_COOP(k_forest_pipe, 32, false, 1); break;
+            case 7: NLF_LAUNCH_COOP(k_forest_pipe, 32, false, 3); break;
+            default: NLF_LAUNCH_COOP(k_forest_pipe, 32, false, 2); break;
         }
 #undef NLF_LAUNCH_COOP
         NLF_CUDA(cudaGetLastError());

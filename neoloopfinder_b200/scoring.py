@@ -403,6 +403,7 @@ def score_and_pool(batch: ScoreBatch, forest, exp_arr, thre: float, res: int, mi
 
 PIPELINE_MIN_JOBS = 8       # matrices per sub-batch below which splitting a batch stops paying
 PIPELINE_DEPTH = 4          # sub-batches of one score_matrices call
+PIPELINE_FIRST = 0.5        # size of the first sub-batch relative to an even split
 
 
 def score_matrices(mats: Sequence[np.ndarray], forest, exp_arr, thre: float, res: int, min_count: int = 2,
@@ -420,7 +421,13 @@ def score_matrices(mats: Sequence[np.ndarray], forest, exp_arr, thre: float, res
     if depth is None:
         depth = int(os.environ.get("NLF_PIPELINE_DEPTH", PIPELINE_DEPTH))
     depth = max(1, min(depth, nj // PIPELINE_MIN_JOBS))
-    cuts = [nj * k // depth for k in range(depth + 1)]
+    # the first upload cannot hide under anything: make the first sub-batch smaller than the others
+    first = float(os.environ.get("NLF_PIPELINE_FIRST", PIPELINE_FIRST))
+    if depth > 1:
+        n0 = max(1, int(round(nj / depth * first)))
+        cuts = [0] + [n0 + (nj - n0) * k // (depth - 1) for k in range(depth)]
+    else:
+        cuts = [0, nj]
     # every sub-batch object first: creating one orders the copy stream after the main stream
     batches = [ScoreBatch(4, upper, ctx) for _ in range(depth)]
     try:

@@ -16,11 +16,13 @@ exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
 mats, chains = bench.gap_free_matrices_gpu(clr, lines, expected, ctx)
 pinned = [torch.from_numpy(G).pin_memory() for G in mats]
 host = [t.numpy() for t in pinned]
-for depth in (1, 2, 3, 4, 6):
-    for rep in range(4):
+for depth, first in ((1, 1.0), (2, 1.0), (4, 1.0), (4, 0.5), (4, 0.3), (5, 0.5), (5, 0.3), (6, 0.4)):
+    os.environ["NLF_PIPELINE_FIRST"] = str(first)
+    ts = []
+    for rep in range(8):
         ctx.l2_flush(); ctx.sync()
         t0 = time.perf_counter()
         score_matrices(host, forest, exp_arr, 0.9, 10000, 2, chains, False, 400, ctx, depth=depth)
         ctx.sync()
-        dt = 1e3 * (time.perf_counter() - t0)
-    print("depth %d: e2e step %.2f ms" % (depth, dt))
+        ts.append(1e3 * (time.perf_counter() - t0))
+    print("depth %d first %.1f: e2e step median %.2f ms (min %.2f)" % (depth, first, sorted(ts[2:])[3], min(ts[2:])))
