@@ -357,18 +357,20 @@ def _pool_scored(batches: Sequence[ScoreBatch], thre: float, res: int, min_count
         order = np.argsort(dj_, kind="stable")
     else:
         # bucket key = (job, chain of i, chain of j)   (callers.py:671-683)
-        ci = np.zeros(len(dj_), dtype=np.int64)
-        cj = np.zeros(len(dj_), dtype=np.int64)
+        dj64 = dj_.astype(np.int64)
         if chains is not None:
-            for job in np.unique(dj_):
-                ch = chains[job]
-                if ch is None:
-                    continue
-                sel = dj_ == job
-                ch = np.asarray(ch)
-                ci[sel] = ch[di[sel]]
-                cj[sel] = ch[dj[sel]]
-        key = (dj_.astype(np.int64) << 40) | (ci << 20) | cj
+            arrs = [np.zeros(0, np.int64) if ch is None else np.asarray(ch, dtype=np.int64) for ch in chains]
+            lens = np.fromiter((a.size for a in arrs), np.int64, len(arrs))
+            coff = np.zeros(len(arrs) + 1, np.int64)
+            np.cumsum(lens, out=coff[1:])
+            cat = np.concatenate(arrs + [np.zeros(1, np.int64)])
+            has = lens[dj64] > 0
+            base = np.where(has, coff[dj64], cat.size - 1)
+            ci = cat[base + np.where(has, di, 0)]
+            cj = cat[base + np.where(has, dj, 0)]
+            key = (dj64 << 40) | (ci << 20) | cj
+        else:
+            key = dj64 << 40
         order = np.argsort(key, kind="stable")
         ks = key[order]
         starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
@@ -378,13 +380,13 @@ def _pool_scored(batches: Sequence[ScoreBatch], thre: float, res: int, min_count
         keep[order] = keep_sorted
     loops = [empty] * nj
     sel = order[keep[order]]
-    js = dj_[sel]
     if len(sel):
-        cuts = np.flatnonzero(np.r_[True, js[1:] != js[:-1]])
-        ends = np.r_[cuts[1:], len(sel)]
-        for a, e in zip(cuts, ends):
-            idx = sel[a:e]
-            loops[int(js[a])] = (di[idx], dj[idx], dp[idx])
+        js = dj_[sel]
+        oi, oj, op = di[sel], dj[sel], dp[sel]
+        cuts = np.flatnonzero(np.r_[True, js[1:] != js[:-1]]).tolist()
+        ends = cuts[1:] + [len(sel)]
+        for a, e, job in zip(cuts, ends, js[cuts].tolist()):
+            loops[job] = (oi[a:e], oj[a:e], op[a:e])
     return loops, (n_cand, n_scored, n_don)
 
 
