@@ -258,3 +258,41 @@ def test_adversarial_matrices_match_oracle(seed, n, density, fname, nexp, zero_a
         ofea, ocl = co.getwindow(G, orr, orc, forest.w, exp)
     assert np.array_equal(cl64, ocl) and np.array_equal(fea64, ofea, equal_nan=True)
     batch.close()
+
+
+@pytest.mark.parametrize("n,density,trees,depth", [(330, 0.85, 40, 12), (520, 0.5, 120, None)])
+def test_w7_model_matches_oracle(n, density, trees, depth, gpu):
+    """A 15 x 15 (w=7) model -- the window Peakachu's constructor sizes its band for -- exercises the
+    third instance of the feature kernel (8-row tiles, 225-feature groups) and, with 120 fully grown
+    trees, a forest that needs several shared-memory parts.  The model is trained here on windows
+    of the same matrix so probabilities spread over [0, 1]."""
+    from sklearn.ensemble import RandomForestClassifier
+    from oracle import coracle as co
+    from neoloopfinder_b200.forest import load_forest
+    from neoloopfinder_b200.scoring import ScoreBatch
+    rng = np.random.default_rng(n)
+    G = _random_band_matrix(rng, n, density)
+    exp = 0.4 / (np.arange(501) + 1.0)
+    r, c, _ = co.candidates(G)
+    fea, cl = co.getwindow(G, r, c, 7, exp)
+    assert fea.shape[1] == 225 and len(fea) > 2000
+    pick = rng.choice(len(fea), 3000, replace=False)
+    y = (fea[pick, 112] + 0.3 * rng.random(3000) > np.median(fea[pick, 112]) + 0.15).astype(int)
+    model = RandomForestClassifier(n_estimators=trees, max_depth=depth, random_state=7, n_jobs=1).fit(
+        fea[pick].astype(np.float32), y)
+    forest = load_forest(model, gpu)
+    assert forest.w == 7
+    batch = ScoreBatch(4, 400, gpu)
+    batch.add_dense(G)
+    batch.keep_features(True)
+    batch.score(forest, exp, 0.5)
+    ocl, opr, of32 = co.score_matrix(G, exp, co.sklearn_forest_arrays(model), 7)
+    i, j, p = batch.scored(0)
+    assert np.array_equal(np.stack([i, j], 1), ocl)
+    assert np.array_equal(batch.features32(0).view(np.uint32), of32.view(np.uint32))
+    assert np.array_equal(p, opr)
+    assert np.array_equal(p, model.predict_proba(of32)[:, 1])          # and sklearn itself
+    assert 0.05 < (p >= 0.5).mean() < 0.95
+    fea64, cl64 = batch.getwindow(0, r, c, 7, exp)
+    assert np.array_equal(cl64, cl) and np.array_equal(fea64, fea)
+    batch.close()
