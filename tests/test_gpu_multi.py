@@ -1,0 +1,30 @@
+"""Multi-GPU host scheduler (one thread and one context per GPU, assemblies sharded by estimated
+pixels, no collective): the merged result must not depend on the number of devices.
+Needs two visible GPUs (``gpurun --gpus 2``); skipped on a single-GPU box."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_call_resolution_same_on_one_and_two_gpus():
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.cli import call_resolution, merge_results
+    from neoloopfinder_b200.synth import analytic_expected, make_workload
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    clr, lines = make_workload("simple", res=10000, seed=321, n_assemblies=10, span=1500000)
+    expected = analytic_expected(clr)
+    model = os.path.join(GOLDEN, "forest_w6.joblib")
+    stats1, stats2 = {}, {}
+    one = call_resolution(clr, lines, 1500000, "sweight", 0.5, 2, False, model, expected, devices=[0], stats=stats1)
+    two = call_resolution(clr, lines, 1500000, "sweight", 0.5, 2, False, model, expected, devices=[0, 1], stats=stats2)
+    assert one == two
+    assert stats1["scored"] == stats2["scored"] > 10000
+    assert len(merge_results(two)) > 0
+    # the second device really worked: its context exists and launched kernels
+    assert _lib.Context.get(1).launch_count() > 0
