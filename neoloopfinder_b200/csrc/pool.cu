@@ -26,6 +26,9 @@ struct BucketWs {           // per-bucket workspace carved from one device alloc
     unsigned char *keep;    // [range]
     unsigned char *alive;   // [range]
     int *order;             // [range]
+    int *chain;             // [range]
+    char *axis2;            // second copy of the seven arrays above: the y anchors are found concurrently
+    size_t axis_bytes;
     Anchor *xa, *ya;        // [range] each
     // per point
     int *sl;                // [m] sorted list (point ids)
@@ -123,39 +126,49 @@ __device__ int d_find_anchors(const int *pos, int npos, int res, int min_count, 
         if (amb) *ambiguous = 1;
         return 0;
     }
-    // _select_by_peak_distance
+    // Peak heights are histogram counts (small non-negative integers), so both orderings below are
+    // counting sorts: O(m + max count) for a single thread even on chromosome-sized buckets.
     unsigned char *keep = ws.keep;
     int *order = ws.order;
-    for (int i = 0; i < m; i++) { order[i] = i; keep[i] = 1; }
-    if (ext_order) {
-        for (int i = 0; i < m; i++) order[i] = ext_order[i];
-    } else {
-        for (int i = 1; i < m; i++) {           // stable ascending insertion sort
-            int o = order[i], j = i - 1;
-            while (j >= 0 && prio[order[j]] > prio[o]) { order[j + 1] = order[j]; j--; }
-            order[j + 1] = o;
+    int *cnt = ws.records;                      // scratch until the interval painting starts
+    int maxc = 0;
+    for (int i = 0; i < m; i++) maxc = max(maxc, (int)prio[i]);
+    if (min_dis > 2) {
+        // _select_by_peak_distance: walk the peaks from the highest priority down; the order among
+        // equal priorities is numpy.argsort's (ext_order when the host had to ask), else stable
+        for (int i = 0; i < m; i++) keep[i] = 1;
+        if (ext_order) {
+            for (int i = 0; i < m; i++) order[i] = ext_order[i];
+        } else {
+            for (int c = 0; c <= maxc + 1; c++) cnt[c] = 0;
+            for (int i = 0; i < m; i++) cnt[(int)prio[i] + 1]++;
+            for (int c = 0; c < maxc; c++) cnt[c + 1] += cnt[c];
+            for (int i = 0; i < m; i++) order[cnt[(int)prio[i]]++] = i;       // stable ascending
         }
-    }
-    for (int i = m - 1; i >= 0; i--) {
-        int j = order[i];
-        if (!keep[j]) continue;
-        int k = j - 1;
-        while (k >= 0 && mid[j] - mid[k] < min_dis) { keep[k] = 0; k--; }
-        k = j + 1;
-        while (k < m && mid[k] - mid[j] < min_dis) { keep[k] = 0; k++; }
-    }
-    m2 = 0;
-    for (int i = 0; i < m; i++) if (keep[i]) mid[m2++] = mid[i];
-    m = m2;
-    // sorted_summits.sort(reverse=True) on (count, index)
-    for (int i = 1; i < m; i++) {
-        int p = mid[i], j = i - 1;
-        while (j >= 0 && (sig[mid[j]] < sig[p] || (sig[mid[j]] == sig[p] && mid[j] < p))) { mid[j + 1] = mid[j]; j--; }
-        mid[j + 1] = p;
-    }
+        for (int i = m - 1; i >= 0; i--) {
+            int j = order[i];
+            if (!keep[j]) continue;
+            int k = j - 1;
+            while (k >= 0 && mid[j] - mid[k] < min_dis) { keep[k] = 0; k--; }
+            k = j + 1;
+            while (k < m && mid[k] - mid[j] < min_dis) { keep[k] = 0; k++; }
+        }
+        m2 = 0;
+        for (int i = 0; i < m; i++) if (keep[i]) mid[m2++] = mid[i];
+        m = m2;
+    }   // two local maxima are never adjacent: a distance of 2 bins removes nothing
+    // sorted_summits.sort(reverse=True) on (count, index): stable ascending by count, then reversed
+    for (int c = 0; c <= maxc + 1; c++) cnt[c] = 0;
+    for (int i = 0; i < m; i++) cnt[(int)sig[mid[i]] + 1]++;
+    for (int c = 0; c < maxc; c++) cnt[c + 1] += cnt[c];
+    for (int i = 0; i < m; i++) order[cnt[(int)sig[mid[i]]]++] = mid[i];
+    for (int i = 0; i < m; i++) mid[i] = order[m - 1 - i];
     int *records = ws.records;
     unsigned char *alive = ws.alive;
-    for (int i = 0; i < n; i++) records[i] = -1;
+    // anchors that share a summit are chained (head/next), so "is this exact interval already
+    // there" looks at one short chain instead of every anchor
+    int *head = ws.order, *nextq = ws.chain;
+    for (int i = 0; i < n; i++) { records[i] = -1; head[i] = -1; }
     int na = 0;
     for (int s = 0; s < m; s++) {
         int pk = mid[s];
@@ -175,12 +188,16 @@ __device__ int d_find_anchors(const int *pos, int npos, int res, int min_count, 
                 }
             }
         }
-        int idx = -1;
-        for (int q = 0; q < na; q++)
-            if (alive[q] && out[q].summit == summit && out[q].lb == m_lb && out[q].rb == m_rb) { idx = q; break; }
+        int idx = -1, last = -1;
+        for (int q = head[summit]; q >= 0; q = nextq[q]) {
+            if (idx < 0 && alive[q] && out[q].lb == m_lb && out[q].rb == m_rb) idx = q;
+            last = q;
+        }
         if (idx < 0) {
             idx = na++;
             out[idx].summit = summit; out[idx].lb = m_lb; out[idx].rb = m_rb; alive[idx] = 1;
+            nextq[idx] = -1;
+            if (last >= 0) nextq[last] = idx; else head[summit] = idx;
         }
         for (int b = m_lb; b <= m_rb; b++) records[b] = idx;
     }
@@ -341,15 +358,26 @@ __device__ BucketWs carve(char *base, int range, int m)
     BucketWs w;
     size_t o = 0;
     auto take = [&](size_t bytes) { char *p = base + o; o += (bytes + 15) & ~(size_t)15; return p; };
-    w.sig = (double *)take(sizeof(double) * range);
-    w.prio = (double *)take(sizeof(double) * range);
-    w.mid = (int *)take(sizeof(int) * range);
-    w.records = (int *)take(sizeof(int) * range);
-    w.order = (int *)take(sizeof(int) * range);
+    auto take_axis = [&](BucketWs &v) {
+        v.sig = (double *)take(sizeof(double) * range);
+        v.prio = (double *)take(sizeof(double) * range);
+        v.mid = (int *)take(sizeof(int) * range);
+        v.records = (int *)take(sizeof(int) * range);
+        v.order = (int *)take(sizeof(int) * range);
+        v.chain = (int *)take(sizeof(int) * range);
+        v.keep = (unsigned char *)take(range);
+        v.alive = (unsigned char *)take(range);
+    };
+    take_axis(w);
+    w.axis2 = base + o;
+    {
+        BucketWs dummy;
+        const size_t before = o;
+        take_axis(dummy);
+        w.axis_bytes = o - before;
+    }
     w.xa = (Anchor *)take(sizeof(Anchor) * range);
     w.ya = (Anchor *)take(sizeof(Anchor) * range);
-    w.keep = (unsigned char *)take(range);
-    w.alive = (unsigned char *)take(range);
     w.sl = (int *)take(sizeof(int) * m);
     w.label = (int *)take(sizeof(int) * m);
     w.stack = (int *)take(sizeof(int) * m);
@@ -365,16 +393,30 @@ __device__ BucketWs carve(char *base, int range, int m)
     return w;
 }
 
+__device__ BucketWs axis2_view(const BucketWs &w, int range)
+{
+    BucketWs v = w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *p = w.axis2 + o; o += (bytes + 15) & ~(size_t)15; return p; };
+    v.sig = (double *)take(sizeof(double) * range);
+    v.prio = (double *)take(sizeof(double) * range);
+    v.mid = (int *)take(sizeof(int) * range);
+    v.records = (int *)take(sizeof(int) * range);
+    v.order = (int *)take(sizeof(int) * range);
+    v.chain = (int *)take(sizeof(int) * range);
+    v.keep = (unsigned char *)take(range);
+    v.alive = (unsigned char *)take(range);
+    return v;
+}
+
 }  // namespace
 
 size_t pool_ws_bytes(int range, int m)
 {
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t o = 0;
-    o += al(sizeof(double) * range) * 2;
-    o += al(sizeof(int) * range) * 3;
+    o += 2 * (al(sizeof(double) * range) * 2 + al(sizeof(int) * range) * 4 + al(range) * 2);   // two axis scratch sets
     o += al(sizeof(Anchor) * range) * 2;
-    o += al(range) * 2;
     o += al(sizeof(int) * m) * 5;
     o += al(sizeof(int) * (m + 1));
     o += al(m) * 3;
@@ -416,10 +458,13 @@ __global__ void __launch_bounds__(256) k_pool(PoolArgs A)
     const int tid = threadIdx.x, nt = blockDim.x;
     __shared__ int s_nxa, s_nya;
     for (int a = tid; a < m; a += nt) { ws.visited[a] = 0; ws.is_final[a] = 0; }
+    // the two anchor searches are sequential algorithms: one thread each, in different warps
     if (tid == 0) {
         s_nxa = d_find_anchors(pi, m, A.res, A.min_count, A.r_bp, ws, ws.xa, A.x_order ? A.x_order + A.xo_off[bk] : nullptr,
                                0, nullptr, nullptr, nullptr);
-        s_nya = d_find_anchors(pj, m, A.res, A.min_count, A.r_bp, ws, ws.ya, A.y_order ? A.y_order + A.yo_off[bk] : nullptr,
+    } else if (tid == 32) {
+        BucketWs wy = axis2_view(ws, A.range[bk]);
+        s_nya = d_find_anchors(pj, m, A.res, A.min_count, A.r_bp, wy, ws.ya, A.y_order ? A.y_order + A.yo_off[bk] : nullptr,
                                0, nullptr, nullptr, nullptr);
     }
     __syncthreads();
