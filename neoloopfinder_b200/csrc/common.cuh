@@ -258,6 +258,24 @@ struct nlf_ctx {
     }
 };
 
+// A sample's pixel table resident on the device (pixels.cu): cooler's CSR layout, bin1 <= bin2.
+struct nlf_pixels {
+    nlf_ctx *ctx = nullptr;
+    long long nbins = 0, nnz = 0;
+    long long *d_off = nullptr;      // [nbins+1]
+    int *d_bin2 = nullptr;           // [nnz] ascending inside a row
+    int *d_cnt = nullptr;            // [nnz]
+    double *d_w = nullptr;           // [nbins] balancing weight per bin (NaN = masked bin)
+};
+// internal entry points of pixels.cu used by norm.cu / expected.cu / score.cu
+int nlf_pixels_fill_assembly(nlf_pixels *px, int balance, const long long *src_lo, const long long *src_hi,
+                             const unsigned char *rev, const int *out_lo, int nblk, int n, const int *d_blk,
+                             double *d_M, double *d_bias);
+int nlf_pixels_chrom_band(nlf_pixels *px, int balance, long long lo, long long hi, int nd, double *d_band,
+                          unsigned char *d_valid);
+int nlf_pixels_export_band(nlf_pixels *px, int balance, long long lo, long long hi, int bw, int pitch,
+                           double **d_band_out, std::vector<int> &kept);
+
 // RAII-free helper: launch bracket used as  { KLaunch k(ctx, cls); kernel<<<...>>>(...); }
 struct KLaunch {
     nlf_ctx *c; int cls; cudaEvent_t a = nullptr; cudaStream_t s;

@@ -139,11 +139,9 @@ __global__ void k_dense_out(const double *__restrict__ M, int n, const int *__re
     out[(size_t)i * nk + j] = scaled_value(M, n, blk, op, val, nblk, r, c);
 }
 
-NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const double *bias, const int *blk_lo,
-                                   const int *blk_hi, int nblk, nlf_assembly **out)
+// block table checks + device allocations shared by the two constructors
+static int assembly_alloc(nlf_ctx *ctx, int n, const int *blk_lo, const int *blk_hi, int nblk, nlf_assembly **out)
 {
-    if (!ctx || !M || !bias || !blk_lo || !blk_hi || !out || n <= 0 || nblk <= 0)
-        return fail(NLF_ERR_ARG, "nlf_assembly_create: bad arguments");
     if (n > 65535) return fail(NLF_ERR_ARG, "assembly of %d bins exceeds the dense limit 65535", n);
     std::vector<int> blk(n, -1);
     for (int b = 0; b < nblk; b++) {
@@ -172,12 +170,76 @@ NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const d
     NLF_CUDA(cudaMallocAsync(&a->d_bhi, sizeof(int) * nblk, s));
     NLF_CUDA(cudaMemcpyAsync(a->d_blo, blk_lo, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(a->d_bhi, blk_hi, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(a->d_M, M, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(a->d_blk, blk.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemsetAsync(a->d_op, 0, sizeof(int) * nblk * nblk, s));
     NLF_CUDA(cudaMemsetAsync(a->d_val, 0, sizeof(double) * nblk * nblk, s));
+    // (pageable sources are staged before cudaMemcpyAsync returns: `blk` may go out of scope)
     *out = a;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const double *bias, const int *blk_lo,
+                                   const int *blk_hi, int nblk, nlf_assembly **out)
+{
+    if (!ctx || !M || !bias || !blk_lo || !blk_hi || !out || n <= 0 || nblk <= 0)
+        return fail(NLF_ERR_ARG, "nlf_assembly_create: bad arguments");
+    nlf_assembly *a = nullptr;
+    int rc = assembly_alloc(ctx, n, blk_lo, blk_hi, nblk, &a);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    NLF_CUDA(cudaMemcpyAsync(a->d_M, M, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    *out = a;
+    return NLF_OK;
+}
+
+// complexSV.reorganize_matrix on the device (assembly.py:408-492): block b = global bins
+// [src_lo[b], src_hi[b]) of the resident pixel table, reversed when rev[b]
+NLF_EXPORT int nlf_assembly_create_from_pixels(nlf_ctx *ctx, nlf_pixels *px, int balance, const int64_t *src_lo,
+                                               const int64_t *src_hi, const uint8_t *rev, int nblk, nlf_assembly **out)
+{
+    if (!ctx || !px || !src_lo || !src_hi || !rev || !out || nblk <= 0)
+        return fail(NLF_ERR_ARG, "nlf_assembly_create_from_pixels: bad arguments");
+    if (px->ctx != ctx) return fail(NLF_ERR_ARG, "nlf_assembly_create_from_pixels: pixel table lives on another context");
+    std::vector<int> blo(nblk), bhi(nblk);
+    std::vector<long long> lo(nblk), hi(nblk);
+    long long n = 0;
+    for (int b = 0; b < nblk; b++) {
+        if (src_lo[b] < 0 || src_hi[b] > px->nbins || src_lo[b] > src_hi[b])
+            return fail(NLF_ERR_ARG, "block %d bins [%lld,%lld) outside the pixel table [0,%lld)", b, (long long)src_lo[b],
+                        (long long)src_hi[b], px->nbins);
+        lo[b] = src_lo[b]; hi[b] = src_hi[b];
+        blo[b] = (int)n;
+        n += src_hi[b] - src_lo[b];
+        if (n > 65535) return fail(NLF_ERR_ARG, "assembly exceeds the dense limit of 65535 bins");
+        bhi[b] = (int)n;
+    }
+    if (n <= 0) return fail(NLF_ERR_ARG, "nlf_assembly_create_from_pixels: empty assembly");
+    nlf_assembly *a = nullptr;
+    int rc = assembly_alloc(ctx, (int)n, blo.data(), bhi.data(), nblk, &a);
+    if (rc) return rc;
+    rc = nlf_pixels_fill_assembly(px, balance, lo.data(), hi.data(), rev, blo.data(), nblk, (int)n, a->d_blk, a->d_M, a->d_bias);
+    if (rc) { nlf_assembly_destroy(a); return rc; }
+    *out = a;
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_size(nlf_assembly *a, int *n)
+{
+    if (!a || !n) return fail(NLF_ERR_ARG, "nlf_assembly_size: NULL argument");
+    *n = a->n;
+    return NLF_OK;
+}
+
+// complexSV.fusion_matrix / complexSV.bias (assembly.py:483-485) back on the host
+NLF_EXPORT int nlf_assembly_fetch_matrix(nlf_assembly *a, double *M, double *bias)
+{
+    if (!a || (!M && !bias)) return fail(NLF_ERR_ARG, "nlf_assembly_fetch_matrix: NULL argument");
+    NLF_CUDA(cudaSetDevice(a->ctx->device));
+    cudaStream_t s = a->ctx->stream;
+    if (M) NLF_CUDA(cudaMemcpyAsync(M, a->d_M, sizeof(double) * (size_t)a->n * a->n, cudaMemcpyDeviceToHost, s));
+    if (bias) NLF_CUDA(cudaMemcpyAsync(bias, a->d_bias, sizeof(double) * a->n, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
     return NLF_OK;
 }
 
