@@ -33,6 +33,7 @@ typedef struct nlf_ctx nlf_ctx;
 typedef struct nlf_forest nlf_forest;
 typedef struct nlf_assembly nlf_assembly;
 typedef struct nlf_batch nlf_batch;
+typedef struct nlf_pixels nlf_pixels;
 
 /* ---- library / context ----------------------------------------------------------------- */
 int nlf_version(void);
@@ -70,12 +71,34 @@ int nlf_forest_destroy(nlf_forest *f);
 /* predict_proba(X)[:, 1] for host float32 rows (N x n_features), results to proba[N]. */
 int nlf_forest_predict(nlf_forest *f, const float *X, long long N, double *proba);
 
+/* ---- resident pixel table: replaces the cooler reads behind
+ *      clr.matrix(balance=col).fetch(r1, r2) and clr.bins().fetch(r)[col]
+ *      (neoloop/assembly.py:387-406, neoloop/util.py:408-413).  The sample is uploaded ONCE in
+ *      cooler's own pixel layout: bin1_offset[nbins+1] (the `indexes/bin1_offset` CSR index),
+ *      bin2[nnz] strictly ascending inside a row with bin1 <= bin2, count[nnz] (int32, cooler's
+ *      dtype), and one weight per bin (the chosen balancing column, NaN = masked bin; also the
+ *      source of complexSV.bias).  Balanced values are (count * w[row bin]) * w[column bin]. ---- */
+int nlf_pixels_create(nlf_ctx *ctx, long long nbins, const int64_t *bin1_offset, const int32_t *bin2,
+                      const int32_t *count, const double *weights, nlf_pixels **out);
+int nlf_pixels_destroy(nlf_pixels *px);
+
 /* ---- assembly normalisation: replaces complexSV.correct_heterozygosity and
  *      Fusion.remove_gaps (neoloop/assembly.py:495-571, neoloop/callers.py:348-367, 504-522).
  * M is the n x n row-major np.triu fusion matrix (assembly.py:483), bias the per-bin
  * weights (NaN already 0), blk_lo/blk_hi the block index ranges (complexSV.index). -------- */
 int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const double *bias,
                         const int *blk_lo, const int *blk_hi, int nblk, nlf_assembly **out);
+/* complexSV.reorganize_matrix on the device (assembly.py:408-492): block b of the assembly is the
+ * global bin range [src_lo[b], src_hi[b]) of the pixel table, traversed in reverse when rev[b]
+ * (orientation '-').  Builds np.triu of the rearranged matrix (NaN -> 0 when balance != 0) and
+ * the bias vector (get_bias, assembly.py:387-397) without any host matrix.  balance = 0 uses raw
+ * counts (balance_type False). */
+int nlf_assembly_create_from_pixels(nlf_ctx *ctx, nlf_pixels *px, int balance, const int64_t *src_lo,
+                                    const int64_t *src_hi, const uint8_t *rev, int nblk,
+                                    nlf_assembly **out);
+int nlf_assembly_size(nlf_assembly *a, int *n);
+/* complexSV.fusion_matrix (n x n) and complexSV.bias (n) back on the host; either may be NULL. */
+int nlf_assembly_fetch_matrix(nlf_assembly *a, double *M, double *bias);
 /* Fusion._extract_xy for every block pair j1<=j2 (pair index p = position in that nested
  * order) up to maxdiag diagonals: mean_out[p*(maxdiag+1)+i] = mean of valid pixels on
  * diagonal i (numpy summation order) when at least mink are valid and the mean is > 0,
@@ -97,6 +120,11 @@ int nlf_assembly_destroy(nlf_assembly *a);
 int nlf_expected_diagonals(nlf_ctx *ctx, const double *band, int n, int nd, const uint8_t *valid,
                            double *sum_out, long long *cnt_out);
 
+/* The same from the resident pixel table, chromosome = global bins [lo, hi): band, valid mask
+ * (weight finite and > 0, util.py:415) and sums never leave the device. */
+int nlf_expected_from_pixels(nlf_ctx *ctx, nlf_pixels *px, int balance, long long lo, long long hi,
+                             int nd, double *sum_out, long long *cnt_out);
+
 /* ---- scoring: replaces Peakachu.__init__/get_candidates/getwindow/predict up to the
  *      Donuts dictionary (neoloop/callers.py:527-628) and util.distance_normalize /
  *      distance_normaize_core / image_normalize (neoloop/util.py:470-524) for a BATCH of
@@ -112,6 +140,12 @@ int nlf_batch_add_assembly(nlf_batch *b, nlf_assembly *a);
 /* Add a matrix given as its band: band[r*pitch + d] = G[r, r+d], d < upper+14 (banded
  * genome-wide input). */
 int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int pitch);
+/* Add a whole chromosome (global bins [lo, hi) of a resident pixel table) as a trivial assembly:
+ * Fusion.remove_gaps (callers.py:504-522; a column is a gap when it holds no non-zero value) and
+ * the finite band of the gap-free matrix (callers.py:527-535) are built on the device.
+ * kept_out[k] = bin, relative to lo, behind gap-free index k (capacity hi - lo); *n_kept = n'. */
+int nlf_batch_add_pixels(nlf_batch *b, nlf_pixels *px, int balance, long long lo, long long hi,
+                         int *kept_out, int *n_kept);
 /* Keep the float32 feature rows addressable after scoring (needed by
  * nlf_batch_fetch_features32; costs one int per band cell).  Call before nlf_batch_score. */
 int nlf_batch_keep_features(nlf_batch *b, int on);

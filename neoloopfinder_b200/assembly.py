@@ -42,6 +42,7 @@ class complexSV(Fusion):
         self._gap_free = None
         self._hcm = None
         self._scale_plan = None
+        self._fusion_matrix = None
 
         self.parse_input(candidate)
         self.tb, self.to = [], []
@@ -164,7 +165,18 @@ class complexSV(Fusion):
         self._gap_free = None
         self._hcm = None
         self._n_bins = n
+        self._fusion_matrix = None
         if map_only:
+            return
+        if hasattr(self.clr, "device_pixels") and n > 0:
+            # the sample's pixel table is resident in HBM; the rearranged matrix
+            # and the bias vector are built there (no region fetches, no host n x n matrix, no upload)
+            col = 'weight' if self.balance_type == False else self.balance_type   # noqa: E712
+            px = self.clr.device_pixels(getattr(self, '_ctx', None), col)
+            lo_hi = [self.clr.global_bins(*self.clr._bin_extent(tuple(r))) for r in blocks]
+            self._asm = DeviceAssembly.from_pixels(px, [a for a, _b in lo_hi], [b for _a, b in lo_hi],
+                                                   [o == '-' for o in orients], balance=bool(self.balance_type))
+            self.bias = self._asm.bias()
             return
         M = np.zeros((n, n))
         bias_parts = []
@@ -183,6 +195,18 @@ class complexSV(Fusion):
 
         self.fusion_matrix = np.triu(M)
         self.bias = np.concatenate(bias_parts) if bias_parts else np.r_[[]]
+
+    @property
+    def fusion_matrix(self):
+        """np.triu of the rearranged matrix (assembly.py:483); fetched from the device on first use
+        when the assembly was built from a resident pixel table."""
+        if self._fusion_matrix is None and self._asm is not None:
+            self._fusion_matrix = self._asm.fusion_matrix()
+        return self._fusion_matrix
+
+    @fusion_matrix.setter
+    def fusion_matrix(self, M):
+        self._fusion_matrix = M
 
     # ------------------------------------------------------------------ device plumbing
     def _device_assembly(self) -> DeviceAssembly:

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnlf_b200.so")
-SOURCES = ["score.cu", "norm.cu", "pool.cu", "expected.cu"]
+SOURCES = ["score.cu", "norm.cu", "pool.cu", "expected.cu", "pixels.cu"]
 
 
 def _newest_source_mtime() -> float:

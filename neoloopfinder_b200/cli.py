@@ -62,11 +62,11 @@ def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, mod
     for ID in ids:
         fu = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu',
                        expected_values=expected, flexible=False)
+        fu._ctx = ctx
         fu.reorganize_matrix()
-        if len(fu.Map) != fu.fusion_matrix.shape[0]:
+        if len(fu.Map) != fu._n_bins:
             out[ID] = None                         # invalid assembly (scripts/neoloop-caller:196-197)
             continue
-        fu._ctx = ctx
         live.append((ID, fu))
     if not live:
         return out
@@ -92,7 +92,7 @@ def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, mod
     for _ID, fu in live:
         asm = fu._device_assembly()
         batch.add_assembly(asm)
-        chain_of = np.array([fu.chains[k] for k in range(fu.fusion_matrix.shape[0])])
+        chain_of = np.array([fu.chains[k] for k in range(fu._n_bins)])
         chains.append(chain_of[asm.kept_index()])     # chains[index_map[i]] per gap-free bin
     loops_by_job, (n_cand, n_scored, n_don) = score_and_pool(batch, forest, exp_arr, prob, res, mmp, chains, nopool)
     if stats is not None:

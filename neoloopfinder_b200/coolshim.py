@@ -13,7 +13,7 @@ expose exactly the attributes the reference touches on ``clr``:
                                                   (neoloop/assembly.py:387-397, 440; util.py:411-413)
 * ``clr.pixels()[:]['count'].values.sum()``       (scripts/neoloop-caller:251-252)
 
-Two sources are provided:
+Three sources are provided:
 
 ``SyntheticCooler``  a *procedural* map: every pixel count is a deterministic
     hash of (seed, bin1, bin2), so an hg38-sized "file" costs no storage, any
@@ -22,7 +22,13 @@ Two sources are provided:
 ``ArrayCooler``      explicit per-chromosome-pair dense blocks held in memory /
     ``.npz`` (for hand-made test matrices).
 
-Both are picklable (the reference fans out with loky processes).
+``PixelCooler``      cooler's own storage layout -- the genome-wide upper-triangular pixel table
+    (``bin1_offset`` index, ``bin2_id``, ``count``) plus the bin table -- held in memory /
+    ``.npz``.  This is the on-disk format that replaces ``.cool`` here and the only source that can
+    live in HBM: ``device_pixels()`` uploads it once and assemblies, chromosome bands and the
+    expected prologue are then built on the GPU.
+
+All are picklable (the reference fans out with loky processes).
 """
 from __future__ import annotations
 
@@ -32,7 +38,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["SyntheticCooler", "ArrayCooler", "load_cooler", "HG38_CHROMSIZES", "parse_region"]
+__all__ = ["SyntheticCooler", "ArrayCooler", "PixelCooler", "load_cooler", "HG38_CHROMSIZES", "parse_region"]
 
 # hg38 primary assembly; autosomes + X sum to 3 031 042 417, the constant at
 # scripts/neoloop-caller:257.
@@ -570,17 +576,202 @@ class ArrayCooler(_CoolerBase):
         return cls(int(z["binsize"]), sizes, blocks, weights)
 
 
+# ----------------------------------------------------------------------------------
+# cooler's pixel table (host copy + device residency)
+# ----------------------------------------------------------------------------------
+class PixelCooler(_CoolerBase):
+    """Cooler-like view over a genome-wide upper-triangular pixel table in cooler's layout.
+
+    ``bin1_offset[nbins + 1]`` indexes the pixels of every ``bin1`` (cooler's
+    ``indexes/bin1_offset``), ``bin2[nnz]`` ascends inside a row with ``bin1 <= bin2``
+    (global bin ids, chromosomes concatenated in ``chromnames`` order), ``count[nnz]`` is int32.
+    ``weights[col]`` are genome-wide per-bin balancing weights (NaN = masked bin).
+
+    The host methods implement the cooler surface the reference touches (the oracle and the live
+    reference read the very same pixels); ``device_pixels`` hands the table to the GPU once.
+    """
+
+    FORMAT = "nlf-pixel-cooler-v1"
+
+    def __init__(self, binsize, chromsizes, bin1_offset, bin2, count, weights, info=None):
+        super().__init__(binsize, chromsizes)
+        self._offsets = {}
+        off = 0
+        for c in self.chromnames:
+            self._offsets[c] = off
+            off += self._nbins(c)
+        self._total_bins = off
+        self.bin1_offset = np.ascontiguousarray(bin1_offset, dtype=np.int64)
+        self.bin2 = np.ascontiguousarray(bin2, dtype=np.int32)
+        self.count = np.ascontiguousarray(count, dtype=np.int32)
+        if self.bin1_offset.size != off + 1 or self.bin2.size != self.count.size or int(self.bin1_offset[-1]) != self.bin2.size:
+            raise ValueError("inconsistent pixel table")
+        self._w = {col: np.ascontiguousarray(a, dtype=np.float64) for col, a in weights.items()}
+        for col, a in self._w.items():
+            if a.size != off:
+                raise ValueError(f"weight column {col!r} has {a.size} entries for {off} bins")
+        self._info = dict(info) if info else None
+        self._device = {}
+        self._csr = None
+
+    # -- pickling: device handles and the scipy view stay behind ---------------------------------
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_device"] = {}
+        st["_csr"] = None
+        return st
+
+    # -- construction ------------------------------------------------------------------------------
+    @classmethod
+    def from_cooler(cls, clr, band_bins: Optional[int] = None, trans: bool = True, row_chunk: int = 2048):
+        """Materialise the pixel table of any cooler-like source.  ``band_bins`` keeps only
+        intra-chromosomal pixels with ``bin2 - bin1 <= band_bins``; ``trans=False`` drops
+        inter-chromosomal pixels (enough for the genome-wide call and the expected prologue)."""
+        names = list(clr.chromnames)
+        sizes = {c: int(clr.chromsizes[c]) for c in names}
+        res = int(clr.binsize)
+        nb = {c: int(math.ceil(sizes[c] / res)) for c in names}
+        offs, off = {}, 0
+        for c in names:
+            offs[c] = off
+            off += nb[c]
+        rows_b2, rows_cnt, indptr = [], [], [0]
+        nnz = 0
+        for i1, c1 in enumerate(names):
+            n1 = nb[c1]
+            for lo in range(0, n1, row_chunk):
+                hi = min(n1, lo + row_chunk)
+                per_row_b2 = [[] for _ in range(hi - lo)]
+                per_row_cnt = [[] for _ in range(hi - lo)]
+                for c2 in names[i1:]:
+                    if c2 != c1 and not trans:
+                        continue
+                    n2 = nb[c2]
+                    if c2 == c1:
+                        clo = lo
+                        chi = n2 if band_bins is None else min(n2, hi + band_bins)
+                    else:
+                        clo, chi = 0, n2
+                    if chi <= clo:
+                        continue
+                    B = np.asarray(clr._raw_block(c1, lo, hi, c2, clo, chi)) if hasattr(clr, "_raw_block") else \
+                        np.nan_to_num(np.asarray(clr.matrix(balance=False).fetch((c1, lo * res, min(hi * res, sizes[c1])),
+                                                                                 (c2, clo * res, min(chi * res, sizes[c2])))))
+                    if not np.array_equal(B, np.round(B)):
+                        raise ValueError("PixelCooler stores integer counts (cooler's int32 `count` column)")
+                    rr, cc = np.nonzero(B)
+                    if c2 == c1:
+                        keep = (cc + clo) >= (rr + lo)
+                        if band_bins is not None:
+                            keep &= (cc + clo) - (rr + lo) <= band_bins
+                        rr, cc = rr[keep], cc[keep]
+                    vals = B[rr, cc].astype(np.int32)
+                    gcol = (cc + clo + offs[c2]).astype(np.int32)
+                    # np.nonzero is row-major: split per row
+                    cuts = np.searchsorted(rr, np.arange(hi - lo + 1))
+                    for k in range(hi - lo):
+                        a, b = cuts[k], cuts[k + 1]
+                        if b > a:
+                            per_row_b2[k].append(gcol[a:b])
+                            per_row_cnt[k].append(vals[a:b])
+                for k in range(hi - lo):
+                    if per_row_b2[k]:
+                        b2 = np.concatenate(per_row_b2[k])
+                        rows_b2.append(b2)
+                        rows_cnt.append(np.concatenate(per_row_cnt[k]))
+                        nnz += b2.size
+                    indptr.append(nnz)
+        bin2 = np.concatenate(rows_b2) if rows_b2 else np.zeros(0, np.int32)
+        count = np.concatenate(rows_cnt) if rows_cnt else np.zeros(0, np.int32)
+        weights = {}
+        for col in ("weight", "sweight"):
+            weights[col] = np.concatenate([np.asarray(clr.bins().fetch(c)[col].values, dtype=np.float64) for c in names])
+        return cls(res, sizes, np.asarray(indptr, dtype=np.int64), bin2, count, weights)
+
+    def save(self, path):
+        payload = {"format": np.array(self.FORMAT), "binsize": np.int64(self.binsize),
+                   "chromnames": np.array(self.chromnames),
+                   "chromsizes": np.array([self._chromsizes[c] for c in self.chromnames], dtype=np.int64),
+                   "bin1_offset": self.bin1_offset, "bin2": self.bin2, "count": self.count}
+        for col, a in self._w.items():
+            payload[f"w|{col}"] = a
+        np.savez_compressed(path, **payload)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, allow_pickle=False)
+        names = [str(x) for x in z["chromnames"]]
+        sizes = dict(zip(names, (int(x) for x in z["chromsizes"])))
+        weights = {k.split("|")[1]: z[k] for k in z.files if k.startswith("w|")}
+        return cls(int(z["binsize"]), sizes, z["bin1_offset"], z["bin2"], z["count"], weights)
+
+    # -- cooler surface ----------------------------------------------------------------------------
+    @property
+    def info(self):
+        if self._info is not None:
+            return self._info
+        return {"sum": int(self.count.sum(dtype=np.int64)), "nnz": int(self.count.size)}
+
+    def _weights(self, c, lo, hi, col):
+        if col not in self._w:
+            col = "weight"
+        o = self._offsets[c]
+        return np.array(self._w[col][o + lo:o + hi], dtype=np.float64, copy=True)
+
+    def _upper(self):
+        if self._csr is None:
+            from scipy import sparse as sp
+            n = self._total_bins
+            self._csr = sp.csr_matrix((self.count.astype(np.float64), self.bin2, self.bin1_offset), shape=(n, n))
+        return self._csr
+
+    def _raw_block(self, c1, lo1, hi1, c2, lo2, hi2):
+        """Symmetric completion of the stored upper triangle restricted to a rectangle."""
+        U = self._upper()
+        a0, a1 = self._offsets[c1] + lo1, self._offsets[c1] + hi1
+        b0, b1 = self._offsets[c2] + lo2, self._offsets[c2] + hi2
+        B = U[a0:a1, b0:b1].toarray() + U[b0:b1, a0:a1].toarray().T
+        # a stored diagonal pixel (g, g) was added twice where the two ranges overlap
+        g0, g1 = max(a0, b0), min(a1, b1)
+        if g1 > g0:
+            g = np.arange(g0, g1)
+            B[g - a0, g - b0] -= U.diagonal()[g0:g1]
+        return B
+
+    # -- device residency --------------------------------------------------------------------------
+    def global_bins(self, chrom, lo_bin, hi_bin):
+        o = self._offsets[chrom]
+        return o + int(lo_bin), o + int(hi_bin)
+
+    def device_pixels(self, ctx=None, col="sweight"):
+        """The table in HBM (one upload per process, GPU and weight column)."""
+        import os
+        from . import _lib
+        from .scoring import DevicePixels
+        ctx = ctx or _lib.Context.get()
+        if col in (True, False, None):
+            col = "weight"                # balance=True / raw counts: the bias column of the reference
+        if col not in self._w:
+            col = "weight"
+        key = (os.getpid(), ctx.device, col)
+        if key not in self._device:
+            self._device[key] = DevicePixels(self.bin1_offset, self.bin2, self.count, self._w[col], ctx)
+        return self._device[key]
+
+
 def load_cooler(uri: str):
     """Open a contact map given on the ``-H`` command line.
 
-    ``*.json``  SyntheticCooler spec; ``*.npz`` ArrayCooler.  Real ``.cool``/``.mcool``
+    ``*.json``  SyntheticCooler spec; ``*.npz`` PixelCooler (pixel table) or ArrayCooler (dense blocks).  Real ``.cool``/``.mcool``
     URIs need the ``cooler`` package, which is tried last and reported if absent.
     """
     if uri.endswith(".json"):
         with open(uri) as fh:
             return SyntheticCooler.from_spec(json.load(fh))
     if uri.endswith(".npz"):
-        return ArrayCooler.load(uri)
+        with np.load(uri, allow_pickle=False) as z:
+            is_pixels = "format" in z.files and str(z["format"]) == PixelCooler.FORMAT
+        return PixelCooler.load(uri) if is_pixels else ArrayCooler.load(uri)
     try:
         import cooler  # type: ignore
     except ImportError as exc:  # pragma: no cover - depends on the image

@@ -35,59 +35,79 @@ __device__ __forceinline__ double scaled_value(const double *__restrict__ M, int
     return v;
 }
 
-// K2a: one thread per (pair, diagonal): gather the valid pixels in row order into scratch.
-// scratch[k * stride + pair*(maxdiag+1) + i] so that neighbouring diagonals are neighbours in memory.
-__global__ void k_pair_compact(const double *__restrict__ M, int n, const double *__restrict__ bias,
-                               const int *__restrict__ pair_lo1, const int *__restrict__ pair_hi1,
-                               const int *__restrict__ pair_lo2, const int *__restrict__ pair_hi2, int npairs,
-                               int maxdiag, double *__restrict__ scratch, size_t stride, int *__restrict__ cnt)
+// K2: one WARP per (pair, diagonal).  The lanes walk the diagonal 32 rows at a time, a ballot
+// keeps the valid pixels in row order (scratch row of the warp), then lanes 0-7 add them in numpy's
+// pairwise order and lane 0 publishes the mean.  (The first version used one thread per diagonal, serial
+// over all rows, and a second kernel for the means: 148 + 83 us per assembly on cfg2.)
+__global__ void __launch_bounds__(256) k_pair_diag_means(const double *__restrict__ M, int n, const double *__restrict__ bias,
+                                  const int *__restrict__ pair_lo1, const int *__restrict__ pair_hi1,
+                                  const int *__restrict__ pair_lo2, const int *__restrict__ pair_hi2, int npairs,
+                                  int maxdiag, int mink, double *__restrict__ scratch, int maxlen,
+                                  int *__restrict__ cnt, double *__restrict__ mean)
 {
-    int p = blockIdx.y;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > maxdiag) return;
-    int idx = p * (maxdiag + 1) + i;
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nd = maxdiag + 1;
+    if (wid >= npairs * nd) return;
+    const int lane = threadIdx.x & 31;
+    const int p = wid / nd, i = wid % nd;
+    double *my = scratch + (size_t)wid * maxlen;
     int k = 0;
     if (i >= 2 && i < n - 1) {          // for i in range(2, M.shape[0]-1)
-        int lo1 = pair_lo1[p], hi1 = pair_hi1[p], lo2 = pair_lo2[p], hi2 = pair_hi2[p];
-        int xs = max(lo1, lo2 - i), xe = min(hi1, min(hi2, n) - i);
-        for (int x = xs; x < xe; x++) {
-            int y = x + i;
-            if (__dmul_rn(bias[x], bias[y]) > 0) {
-                scratch[(size_t)k * stride + idx] = M[(size_t)x * n + y];
-                k++;
-            }
+        const int lo1 = pair_lo1[p], hi1 = pair_hi1[p], lo2 = pair_lo2[p], hi2 = pair_hi2[p];
+        const int xs = max(lo1, lo2 - i), xe = min(hi1, min(hi2, n) - i);
+        for (int base = xs; base < xe; base += 32) {
+            const int x = base + lane;
+            bool ok = false;
+            if (x < xe) ok = __dmul_rn(bias[x], bias[x + i]) > 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) my[k + __popc(mask & ((1u << lane) - 1u))] = M[(size_t)x * n + x + i];
+            k += __popc(mask);
         }
     }
-    cnt[idx] = k;
-}
-
-// K2b: numpy mean of the gathered values
-__global__ void k_pair_means(const double *__restrict__ scratch, size_t stride, const int *__restrict__ cnt,
-                             int total, int mink, double *__restrict__ mean)
-{
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    int c = cnt[idx];
+    __syncwarp();
     double m = __longlong_as_double(0x7ff8000000000000LL);
-    if (c >= mink && c > 0) {
-        const double *base = scratch + idx;
-        double s = np_pairwise_sum([=](int k) { return base[(size_t)k * stride]; }, c);
-        double mm = __ddiv_rn(s, (double)c);
+    if (k >= mink && k > 0 && lane < 8) {
+        const double s = np_pairwise_sum_group8([&](int e) { return my[e]; }, k, lane, 0xffu);
+        const double mm = __ddiv_rn(s, (double)k);
         if (mm > 0) m = mm;
     }
-    mean[idx] = m;
+    if (lane == 0) {
+        cnt[wid] = k;
+        mean[wid] = m;
+    }
 }
 
-// K4a: column sums of hcm in numpy's axis-0 order (row after row), one thread per column.
+// K4a fast path: per column, does hcm hold a positive entry (bit 0) / a negative or NaN entry (bit 1)?
+// A column without bit 1 sums to zero exactly when it has no positive entry (a sum of non-negative
+// doubles with one positive term cannot round to 0), whatever the order; columns with bit 1 take the
+// sequential kernel below, which follows numpy's axis-0 order.  Fully parallel, one pass over M.
+__global__ void k_gap_flags(const double *__restrict__ M, int n, const int *__restrict__ blk,
+                            const int *__restrict__ op, const double *__restrict__ val, int nblk,
+                            int *__restrict__ flags)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    if (j >= n) return;
+    const int r0 = blockIdx.y * 64, r1 = min(r0 + 64, n);
+    int f = 0;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+        const double v = scaled_value(M, n, blk, op, val, nblk, r, j);
+        if (v > 0) f |= 1;
+        else if (!(v == 0)) f |= 2;
+    }
+    if (f) atomicOr(&flags[j], f);
+}
+
+// K4a exact path: column sums of hcm in numpy's axis-0 order (row after row), one thread per listed column.
 // The rescale rule only changes at block boundaries, so the loop runs block by block with the
 // rule in registers and eight independent loads in flight; the additions stay strictly sequential.
 __global__ void k_gap_columns(const double *__restrict__ M, int n, const int *__restrict__ blk,
                               const int *__restrict__ blo, const int *__restrict__ bhi,
                               const int *__restrict__ op, const double *__restrict__ val, int nblk,
-                              unsigned char *__restrict__ is_gap)
+                              const int *__restrict__ cols, int ncols, unsigned char *__restrict__ is_gap)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncols) return;
+    const int j = cols ? cols[t] : t;
     const int bj = blk[j];
     double s = 0.0;
     bool first = true;
@@ -108,7 +128,7 @@ __global__ void k_gap_columns(const double *__restrict__ M, int n, const int *__
         }
         for (; r < re; r++) s = __dadd_rn(s, sc(col[(size_t)r * n]));
     }
-    is_gap[j] = (s == 0) ? 1 : 0;
+    is_gap[t] = (s == 0) ? 1 : 0;
 }
 
 // K4b: gap-free band straight from the fusion matrix: band[i][d] = hcm[kept[i]][kept[i+d]]
@@ -259,26 +279,21 @@ NLF_EXPORT int nlf_assembly_diag_means(nlf_assembly *a, int maxdiag, int mink, d
             maxlen = std::max(maxlen, a->bhi[j1] - a->blo[j1]);
         }
     const int total = npairs * nd;
-    const size_t stride = (size_t)total;
     int *d_par, *d_cnt;
     double *d_scratch, *d_mean;
     NLF_CUDA(cudaMallocAsync(&d_par, sizeof(int) * 4 * npairs, s));
     NLF_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * total, s));
     NLF_CUDA(cudaMallocAsync(&d_mean, sizeof(double) * total, s));
-    NLF_CUDA(cudaMallocAsync(&d_scratch, sizeof(double) * stride * maxlen, s));
+    NLF_CUDA(cudaMallocAsync(&d_scratch, sizeof(double) * (size_t)total * maxlen, s));
     NLF_CUDA(cudaMemcpyAsync(d_par, lo1.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(d_par + npairs, hi1.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(d_par + 2 * npairs, lo2.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(d_par + 3 * npairs, hi2.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
     {
         KLaunch k(c, P_NORM);
-        dim3 grid((nd + 63) / 64, npairs);
-        k_pair_compact<<<grid, 64, 0, s>>>(a->d_M, a->n, a->d_bias, d_par, d_par + npairs, d_par + 2 * npairs,
-                                           d_par + 3 * npairs, npairs, maxdiag, d_scratch, stride, d_cnt);
-    }
-    {
-        KLaunch k(c, P_NORM);
-        k_pair_means<<<(total + 63) / 64, 64, 0, s>>>(d_scratch, stride, d_cnt, total, mink, d_mean);
+        k_pair_diag_means<<<(total + 7) / 8, 256, 0, s>>>(a->d_M, a->n, a->d_bias, d_par, d_par + npairs, d_par + 2 * npairs,
+                                                          d_par + 3 * npairs, npairs, maxdiag, mink, d_scratch, maxlen,
+                                                          d_cnt, d_mean);
     }
     NLF_CUDA(cudaGetLastError());
     NLF_CUDA(cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * total, cudaMemcpyDeviceToHost, s));
@@ -313,17 +328,46 @@ static int ensure_gaps(nlf_assembly *a)
     nlf_ctx *c = a->ctx;
     cudaStream_t s = c->stream;
     const int n = a->n;
-    unsigned char *d_gap;
-    NLF_CUDA(cudaMallocAsync(&d_gap, n, s));
+    int *d_flags;
+    NLF_CUDA(cudaMallocAsync(&d_flags, sizeof(int) * n, s));
+    NLF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * n, s));
     {
         KLaunch k(c, P_NORM);
-        k_gap_columns<<<(n + 31) / 32, 32, 0, s>>>(a->d_M, n, a->d_blk, a->d_blo, a->d_bhi, a->d_op, a->d_val, a->nblk, d_gap);
+        dim3 grid((n + 31) / 32, (n + 63) / 64), block(32, 8);
+        k_gap_flags<<<grid, block, 0, s>>>(a->d_M, n, a->d_blk, a->d_op, a->d_val, a->nblk, d_flags);
     }
     NLF_CUDA(cudaGetLastError());
-    std::vector<unsigned char> gap(n);
-    NLF_CUDA(cudaMemcpyAsync(gap.data(), d_gap, n, cudaMemcpyDeviceToHost, s));
+    std::vector<int> flags(n);
+    NLF_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
     NLF_CUDA(cudaStreamSynchronize(s));
-    NLF_CUDA(cudaFreeAsync(d_gap, s));
+    NLF_CUDA(cudaFreeAsync(d_flags, s));
+    std::vector<unsigned char> gap(n);
+    std::vector<int> exact;
+    for (int j = 0; j < n; j++) {
+        gap[j] = (flags[j] & 1) ? 0 : 1;
+        if (flags[j] & 2) exact.push_back(j);
+    }
+    if (!exact.empty()) {
+        // columns with a negative or NaN entry: the sum in numpy's row order decides
+        const int ne = (int)exact.size();
+        int *d_cols;
+        unsigned char *d_gap;
+        std::vector<unsigned char> g(ne);
+        NLF_CUDA(cudaMallocAsync(&d_cols, sizeof(int) * ne, s));
+        NLF_CUDA(cudaMallocAsync(&d_gap, ne, s));
+        NLF_CUDA(cudaMemcpyAsync(d_cols, exact.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, s));
+        {
+            KLaunch k(c, P_NORM);
+            k_gap_columns<<<(ne + 31) / 32, 32, 0, s>>>(a->d_M, n, a->d_blk, a->d_blo, a->d_bhi, a->d_op, a->d_val, a->nblk,
+                                                         d_cols, ne, d_gap);
+        }
+        NLF_CUDA(cudaGetLastError());
+        NLF_CUDA(cudaMemcpyAsync(g.data(), d_gap, ne, cudaMemcpyDeviceToHost, s));
+        NLF_CUDA(cudaStreamSynchronize(s));
+        NLF_CUDA(cudaFreeAsync(d_cols, s));
+        NLF_CUDA(cudaFreeAsync(d_gap, s));
+        for (int t = 0; t < ne; t++) gap[exact[t]] = g[t];
+    }
     // index bookkeeping of callers.py:509-516 (w = 5: keep every bin when fewer than 11 survive)
     a->kept.clear();
     for (int j = 0; j < n; j++)

@@ -1657,6 +1657,32 @@ NLF_EXPORT int nlf_batch_add_assembly(nlf_batch *b, nlf_assembly *a)
     return (int)b->jobs.size() - 1;
 }
 
+// A whole chromosome (global bins [lo, hi) of the resident pixel table) as a trivial assembly:
+// gap columns removed (callers.py:504-522), the finite band of the gap-free matrix built on the device
+// (callers.py:527-535).  kept_out[k] = bin (relative to lo) behind gap-free index k; capacity hi - lo.
+NLF_EXPORT int nlf_batch_add_pixels(nlf_batch *b, nlf_pixels *px, int balance, long long lo, long long hi,
+                                    int *kept_out, int *n_kept)
+{
+    if (!b || !px || !n_kept || lo < 0 || hi <= lo) return fail(NLF_ERR_ARG, "nlf_batch_add_pixels: bad arguments");
+    if (px->ctx != b->ctx) return fail(NLF_ERR_ARG, "nlf_batch_add_pixels: pixel table lives on another context");
+    if (hi > px->nbins) return fail(NLF_ERR_ARG, "nlf_batch_add_pixels: bins [%lld,%lld) outside [0,%lld)", lo, hi, px->nbins);
+    if (hi - lo > 65535) return fail(NLF_ERR_ARG, "band input limited to n <= 65535 rows per job, got %lld (shard the chromosome)", hi - lo);
+    int rc = check_can_add(b);
+    if (rc) return rc;
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    HostJob j;
+    std::vector<int> kept;
+    rc = nlf_pixels_export_band(px, balance, lo, hi, b->bw, b->pitch, &j.d_band, kept);
+    if (rc) return rc;
+    j.n = (int)kept.size();
+    j.band_big = true;
+    *n_kept = j.n;
+    if (kept_out) memcpy(kept_out, kept.data(), sizeof(int) * kept.size());
+    b->jobs.push_back(j);
+    return (int)b->jobs.size() - 1;
+}
+
 NLF_EXPORT int nlf_batch_njobs(nlf_batch *b) { return b ? (int)b->jobs.size() : 0; }
 
 template <int W>

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, f64, i32, ptr
 
-__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "pool_buckets", "pool_flat", "local_clustering_gpu",
+__all__ = ["gaussian_weights", "ScoreBatch", "DeviceAssembly", "DevicePixels", "pool_buckets", "pool_flat", "local_clustering_gpu",
            "score_and_pool", "score_matrices"]
 
 
@@ -30,8 +30,78 @@ def gaussian_weights(sigma: float = 1.0, truncate: float = 4.0):
     return np.ascontiguousarray(phi[::-1], dtype=np.float64), radius
 
 
+class DevicePixels:
+    """A sample's pixel table resident in HBM (cooler's layout: ``bin1_offset`` CSR index, ``bin2``,
+    ``count`` for bin1 <= bin2, one balancing weight per bin).  Uploaded once per sample, GPU and
+    weight column; assemblies, chromosome bands and the expected prologue are built from it on
+    the device (include/nlf_b200.h, nlf_pixels_*)."""
+
+    def __init__(self, bin1_offset, bin2, count, weights, ctx=None):
+        self.ctx = ctx or _lib.Context.get()
+        off = np.ascontiguousarray(bin1_offset, dtype=np.int64)
+        b2 = np.ascontiguousarray(bin2, dtype=np.int32)
+        cnt = np.ascontiguousarray(count, dtype=np.int32)
+        w = f64(weights)
+        self.nbins = int(w.size)
+        if off.size != self.nbins + 1 or b2.size != cnt.size or (off.size and int(off[-1]) != b2.size):
+            raise ValueError("inconsistent pixel table: bin1_offset / bin2 / count / weights sizes")
+        self.nnz = int(b2.size)
+        self.h = C.c_void_p()
+        check(_lib.load().nlf_pixels_create(self.ctx.h, self.nbins, ptr(off, C.c_int64), ptr(b2, C.c_int),
+                                            ptr(cnt, C.c_int), ptr(w, C.c_double), C.byref(self.h)))
+
+    def expected_diagonals(self, lo: int, hi: int, nd: int, balance: bool = True):
+        """util._prepare_core for the chromosome of global bins [lo, hi): (sums[nd'], counts[nd'])
+        with nd' = min(nd, hi - lo)."""
+        nd = min(int(nd), int(hi) - int(lo))
+        sums = np.empty(nd, dtype=np.float64)
+        cnts = np.empty(nd, dtype=np.int64)
+        check(_lib.load().nlf_expected_from_pixels(self.ctx.h, self.h, 1 if balance else 0, int(lo), int(hi), nd,
+                                                   ptr(sums, C.c_double), ptr(cnts, C.c_longlong)))
+        return sums, cnts
+
+    def close(self):
+        if self.h:
+            _lib.load().nlf_pixels_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceAssembly:
     """Device-resident fusion matrix of one assembly (K2-K4)."""
+
+    @classmethod
+    def from_pixels(cls, pixels: DevicePixels, src_lo, src_hi, reverse, balance: bool = True):
+        """complexSV.reorganize_matrix on the device: block b = global bins [src_lo[b], src_hi[b])
+        of ``pixels``, traversed in reverse when ``reverse[b]``."""
+        self = cls.__new__(cls)
+        self.ctx = pixels.ctx
+        lo = np.ascontiguousarray(src_lo, dtype=np.int64)
+        hi = np.ascontiguousarray(src_hi, dtype=np.int64)
+        rev = np.ascontiguousarray(reverse, dtype=np.uint8)
+        self.nblk = int(lo.size)
+        self.h = C.c_void_p()
+        check(_lib.load().nlf_assembly_create_from_pixels(self.ctx.h, pixels.h, 1 if balance else 0, ptr(lo, C.c_int64),
+                                                          ptr(hi, C.c_int64), ptr(rev, C.c_ubyte), self.nblk,
+                                                          C.byref(self.h)))
+        self.n = int((hi - lo).sum())
+        self._kept = None
+        return self
+
+    def fusion_matrix(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        check(_lib.load().nlf_assembly_fetch_matrix(self.h, ptr(out, C.c_double), None))
+        return out
+
+    def bias(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.float64)
+        check(_lib.load().nlf_assembly_fetch_matrix(self.h, None, ptr(out, C.c_double)))
+        return out
 
     def __init__(self, M, bias, block_index, ctx=None):
         self.ctx = ctx or _lib.Context.get()
@@ -124,6 +194,17 @@ class ScoreBatch:
         self.njobs += 1
         self.n.append(len(asm.kept_index()))
         return j
+
+    def add_pixels(self, pixels: DevicePixels, lo: int, hi: int, balance: bool = True):
+        """A whole chromosome (global bins [lo, hi) of a resident pixel table) as a trivial assembly;
+        returns (job, kept) with kept[k] = bin (relative to lo) behind gap-free index k."""
+        kept = np.empty(int(hi) - int(lo), dtype=np.int32)
+        nk = C.c_int(0)
+        j = check(_lib.load().nlf_batch_add_pixels(self.h, pixels.h, 1 if balance else 0, int(lo), int(hi),
+                                                   ptr(kept, C.c_int), C.byref(nk)))
+        self.njobs += 1
+        self.n.append(nk.value)
+        return j, kept[:nk.value].copy()
 
     def add_band(self, band) -> int:
         band = f64(band)

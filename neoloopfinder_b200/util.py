@@ -56,6 +56,14 @@ def _chrom_diagonal_sums(args):
     import ctypes as C
     from . import _lib
     clr, chrom, maxdis, balance = args
+    if hasattr(clr, "device_pixels"):
+        # resident pixel table: band, valid mask and sums stay on the device
+        col = "weight" if isinstance(balance, bool) else balance
+        px = clr.device_pixels(None, col)
+        n = clr._nbins(chrom)
+        lo, hi = clr.global_bins(chrom, 0, n)
+        sums, cnts = px.expected_diagonals(lo, hi, maxdis + 1, balance=bool(balance))
+        return {i: [np.float64(sums[i]), int(cnts[i])] for i in range(min(n - 1, maxdis) + 1) if cnts[i] > 0}
     band, weights = chrom_band(clr, chrom, maxdis + 1, balance)
     n, nd = band.shape
     band = np.where(np.isfinite(band), band, 0.0)         # masked out below; keep the copy finite

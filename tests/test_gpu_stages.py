@@ -296,3 +296,69 @@ def test_w7_model_matches_oracle(n, density, trees, depth, gpu):
     fea64, cl64 = batch.getwindow(0, r, c, 7, exp)
     assert np.array_equal(cl64, cl) and np.array_equal(fea64, fea)
     batch.close()
+
+
+@pytest.mark.parametrize("seed,sizes", [(0, (700, 650)), (1, (300, 40, 520)), (2, (9, 1100))])
+def test_pair_diagonal_means_long_blocks(seed, sizes, gpu):
+    """K2 with more valid pixels per diagonal than one numpy leaf (128) and ragged blocks, against
+    the port's extract_xy (the reference's masked ``M[x, y].mean()`` per diagonal)."""
+    from neoloopfinder_b200.scoring import DeviceAssembly
+    from oracle import pyport
+    rng = np.random.default_rng(seed)
+    n = sum(sizes)
+    M = np.triu(rng.poisson(4.0, size=(n, n)) * rng.uniform(0.001, 0.02, size=(n, n)))
+    M[rng.random((n, n)) < 0.3] = 0.0
+    bias = rng.uniform(0.05, 0.15, n)
+    bias[rng.random(n) < 0.08] = 0.0
+    edges = np.r_[0, np.cumsum(sizes)]
+    bi = [(int(edges[k]), int(edges[k + 1])) for k in range(len(sizes))]
+    res, maxdiag = 10000, 200
+    asm = DeviceAssembly(M, bias, bi, gpu)
+    mean, cnt = asm.diag_means(maxdiag)
+    valid_bias = np.triu((bias[:, None] * bias) > 0)
+    p = 0
+    for a, ia in enumerate(bi):
+        for b, ib in enumerate(bi):
+            if a > b:
+                continue
+            mask = np.zeros((n, n), dtype=bool)
+            mask[ia[0]:ia[1], ib[0]:ib[1]] = True
+            want = pyport.extract_xy(M, res, mask & valid_bias, maxdis=maxdiag * res, mink=3)
+            got = {int(i): mean[p][i] for i in np.where(~np.isnan(mean[p]))[0]}
+            assert got == want, (a, b)
+            p += 1
+    assert cnt.max() > 128
+    asm.close()
+
+
+def test_gap_columns_with_negative_and_cancelling_entries(gpu):
+    """Fusion.remove_gaps tests ``hcm.sum(axis=0) == 0``: columns whose entries cancel are gaps, columns
+    holding NaN are not; the parallel sign scan hands exactly those columns to the numpy-order sum."""
+    from neoloopfinder_b200.scoring import DeviceAssembly
+    rng = np.random.default_rng(5)
+    n = 150
+    M = np.triu(rng.random((n, n)))
+    M[:, 10] = 0.0                                   # plain gap
+    M[:, 20] = 0.0
+    M[3, 20], M[7, 20] = 1.5, -1.5                   # cancels exactly: gap
+    M[:, 30] = 0.0
+    M[0, 30], M[1, 30], M[2, 30] = 1e16, 1.0, -1e16  # (1e16 + 1) - 1e16 = 0 in row order: gap
+    M[:, 40] = 0.0
+    M[0, 40], M[1, 40], M[2, 40] = 1e16, -1e16, 1.0  # same entries, another order: not a gap
+    M[5, 50] = -M[5, 50]                             # mixed signs, non-zero sum
+    M[:, 60] = 0.0
+    M[2, 60] = np.nan                                # NaN sum != 0: kept
+    M[:, 70] = 0.0
+    M[4, 70] = -0.0
+    bias = np.ones(n)
+    bi = [(0, 80), (80, n)]
+    op = np.array([[1, 2], [0, 1]], np.int32)
+    val = np.array([[2.0, 0.5], [1.0, 4.0]])
+    asm = DeviceAssembly(M, bias, bi, gpu)
+    asm.set_scales(op, val)
+    hcm = asm.hcm()
+    with np.errstate(invalid="ignore"):
+        want = np.where(~(hcm.sum(axis=0) == 0))[0]
+    assert np.array_equal(asm.kept_index(), want)
+    assert not {10, 20, 30, 70} & set(want.tolist()) and {40, 50, 60} <= set(want.tolist())
+    asm.close()

@@ -1,0 +1,100 @@
+"""CPU checks of the pixel-table source: the host view of a
+PixelCooler returns the same regions as the source it was made from, survives save/load and
+pickling, and -- in the build container -- the REAL reference's complexSV.reorganize_matrix and
+_prepare_core give identical results on it."""
+import pickle
+
+import numpy as np
+import pytest
+
+from neoloopfinder_b200.coolshim import PixelCooler, SyntheticCooler, load_cooler
+
+SIZES = {"chr1": 3_000_000, "chr2": 2_000_000, "chr3": 1_500_000}
+SVS = [("chr1", 1_200_000, "+", "chr2", 800_000, "-"), ("chr3", 400_000, "+", "chr3", 900_000, "+")]
+
+
+@pytest.fixture(scope="module")
+def pair():
+    clr = SyntheticCooler(binsize=10000, chromsizes=SIZES, seed=3, svs=SVS)
+    return clr, PixelCooler.from_cooler(clr)
+
+
+def test_fetch_equals_source(pair):
+    clr, px = pair
+    regions = [(("chr1", 0, 1_200_000), ("chr2", 800_000, 2_000_000)),
+               (("chr2", 100_000, 900_000), ("chr1", 50_000, 700_000)),          # transposed rectangle
+               (("chr1", 0, 3_000_000), ("chr1", 0, 3_000_000)),
+               (("chr1", 200_000, 1_000_000), ("chr1", 500_000, 1_500_000)),      # overlapping ranges
+               (("chr3", 905_000, 1_500_000), ("chr3", 0, 400_001))]
+    for r1, r2 in regions:
+        for bal in (False, "weight", "sweight"):
+            assert np.array_equal(clr.matrix(balance=bal).fetch(r1, r2), px.matrix(balance=bal).fetch(r1, r2),
+                                  equal_nan=True), (r1, r2, bal)
+    for c in SIZES:
+        for col in ("weight", "sweight"):
+            assert np.array_equal(clr.bins().fetch(c)[col].values, px.bins().fetch(c)[col].values, equal_nan=True)
+    a = clr.matrix(balance="weight", sparse=True).fetch("chr2").toarray()
+    b = px.matrix(balance="weight", sparse=True).fetch("chr2").toarray()
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_layout_and_roundtrip(pair, tmp_path):
+    _clr, px = pair
+    off, b2 = px.bin1_offset, px.bin2
+    assert off[0] == 0 and off[-1] == b2.size and np.all(np.diff(off) >= 0)
+    rows = np.repeat(np.arange(off.size - 1), np.diff(off))
+    assert np.all(b2 >= rows)                                   # upper triangle
+    same_row = rows[1:] == rows[:-1]
+    assert np.all(b2[1:][same_row] > b2[:-1][same_row])         # strictly ascending inside a row
+    assert px.count.dtype == np.int32 and np.all(px.count > 0)
+    path = str(tmp_path / "m.px.npz")
+    px.save(path)
+    q = load_cooler(path)
+    assert isinstance(q, PixelCooler) and q.chromnames == px.chromnames and q.binsize == px.binsize
+    assert np.array_equal(q.bin1_offset, off) and np.array_equal(q.bin2, b2) and np.array_equal(q.count, px.count)
+    r = pickle.loads(pickle.dumps(px))
+    assert np.array_equal(r.matrix(balance="sweight").fetch("chr3"), px.matrix(balance="sweight").fetch("chr3"),
+                          equal_nan=True)
+
+
+def test_band_limited_table():
+    clr = SyntheticCooler(binsize=10000, chromsizes={"chr1": 2_000_000, "chr2": 900_000}, seed=5)
+    px = PixelCooler.from_cooler(clr, band_bins=50, trans=False)
+    full = np.triu(clr.matrix(balance=False).fetch("chr1"))
+    got = np.triu(px.matrix(balance=False).fetch("chr1"))
+    d = np.subtract.outer(np.arange(full.shape[0]), np.arange(full.shape[0]))
+    assert np.array_equal(got, np.where(-d <= 50, full, 0))
+    assert not px.matrix(balance=False).fetch("chr1", "chr2").any()
+
+
+def test_float_counts_are_refused():
+    from neoloopfinder_b200.coolshim import ArrayCooler
+    B = np.array([[1.5, 0.0], [0.0, 2.0]])
+    arr = ArrayCooler(10000, {"chr1": 20000}, {("chr1", "chr1"): B},
+                      {"weight": {"chr1": np.ones(2)}, "sweight": {"chr1": np.ones(2)}})
+    with pytest.raises(ValueError):
+        PixelCooler.from_cooler(arr)
+
+
+@pytest.mark.reference
+def test_real_reference_reads_the_same_from_the_pixel_table(pair):
+    from oracle.run_reference import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference tree only exists in the build container")
+    _rc, ra, ru, _cli = import_reference()
+    clr, px = pair
+    lines = ["translocation,1,1200000,+,2,800000,-\t1,600000\t2,1400000",
+             "inversion,3,400000,+,3,900000,+\t3,0\t3,500000",
+             "translocation,1,1200000,+,2,800000,-\tinversion,2,1500000,+,3,900000,+\t1,600000\t3,300000"]
+    for line in lines:
+        for col in ("sweight", False):
+            a = ra.complexSV(clr, line, span=600000, col=col, protocol="insitu", expected_values={}, flexible=False)
+            b = ra.complexSV(px, line, span=600000, col=col, protocol="insitu", expected_values={}, flexible=False)
+            a.reorganize_matrix()
+            b.reorganize_matrix()
+            assert np.array_equal(a.fusion_matrix, b.fusion_matrix) and np.array_equal(a.bias, b.bias)
+            assert a.index == b.index and a.Map == b.Map
+    for bal in ("sweight", True, False):
+        ea = ru._prepare_core((clr, "chr1", 250, bal))
+        eb = ru._prepare_core((px, "chr1", 250, bal))
+        assert ea.keys() == eb.keys() and all(ea[k][0] == eb[k][0] and ea[k][1] == eb[k][1] for k in ea)

@@ -8,7 +8,7 @@ import json
 import re
 import sys
 
-PREP = ("k_gap_columns", "k_pair_compact", "k_pair_means", "k_dense_out", "k_gap_band", "k_fp64_peak")
+PREP = ("k_gap_columns", "k_gap_flags", "k_pair_diag_means", "k_pair_compact", "k_pair_means", "k_px_", "k_dense_out", "k_gap_band", "k_fp64_peak")
 
 
 def main():
