@@ -400,6 +400,16 @@ def main():
         forest_info = {
             "kernel": "k_forest_pipe<32 warps, 2 trees per lane> x parts + k_forest_nan", "ms_per_step": forest_ms,
             "node_visits_per_s": 1617.0 * scored_per_step / (forest_ms * 1e-3) if forest_ms else None,
+            # shared-memory roofline of the traversal: a warp node step needs at least 3 wavefronts (one
+            # conflict-free 4-byte feature load + one 8-byte node load = two 128-byte wavefronts); an SM
+            # serves one wavefront per clock
+            "smem_roofline": ({
+                "algorithmic_wavefronts_per_step": 3.0 * 1617.0 * scored_per_step / 32.0,
+                "achieved_gwavefronts_per_s": 3.0 * 1617.0 * scored_per_step / 32.0 / (forest_ms * 1e-3) / 1e9,
+                "peak_gwavefronts_per_s": 148 * 1.965,
+                "frac": 3.0 * 1617.0 * scored_per_step / 32.0 / (forest_ms * 1e-3) / 1e9 / (148 * 1.965),
+                "peak_source": "148 SMs x 1.965 GHz (MEASURED_PEAKS.json sm_max_mhz) x 1 wavefront per clock",
+            } if forest_ms else None),
             "note": "about 1617 node visits per pixel (100 trees, mean leaf depth 16.2); bound by shared-memory "
                     "wavefronts and issue slots, see profiles/r01_ncu_summary.md",
         }
