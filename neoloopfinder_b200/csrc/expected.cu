@@ -35,9 +35,20 @@ __global__ void k_exp_segscan(int nseg, int nd, int *__restrict__ segcnt, int *_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd) return;
     int run = 0;
-    for (int seg = 0; seg < nseg; seg++) {
+    int seg = 0;
+    for (; seg + 8 <= nseg; seg += 8) {             // eight independent loads in flight, then the prefix
+        int c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = segcnt[(size_t)(seg + k) * nd + i];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            segcnt[(size_t)(seg + k) * nd + i] = run;   // exclusive prefix: first slot of the segment
+            run += c[k];
+        }
+    }
+    for (; seg < nseg; seg++) {
         const int c = segcnt[(size_t)seg * nd + i];
-        segcnt[(size_t)seg * nd + i] = run;         // exclusive prefix: first slot of the segment
+        segcnt[(size_t)seg * nd + i] = run;
         run += c;
     }
     cnt[i] = run;

@@ -37,12 +37,30 @@ def gap_free_band(band_wide, ndiag=414):
     return np.ascontiguousarray(out), kept
 
 
+class _Only:
+    """View of a cooler-like source that lists only some chromosomes but keeps the source's pixel values."""
+
+    def __init__(self, clr, names):
+        self._clr = clr
+        self.chromnames = list(names)
+        self.binsize = clr.binsize
+        self.chromsizes = {c: int(clr.chromsizes[c]) for c in names}
+
+    def _raw_block(self, *a):
+        return self._clr._raw_block(*a)
+
+    def bins(self):
+        return self._clr.bins()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chroms", default=None)
     ap.add_argument("--res", type=int, default=5000)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--prob", type=float, default=0.9)
+    ap.add_argument("--pixels", action="store_true",
+                    help="row f-2: the map is a pixel table resident in HBM; gap removal and the bands are built on the GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -58,12 +76,27 @@ def main():
     exp_arr = np.array([exp[i] for i in sorted(exp)])
     t0 = time.perf_counter()
     bands = []
-    for c in mine:
-        bw = clr.fetch_band(c, 450, "sweight")
-        g, kept = gap_free_band(bw)
-        bands.append(g)
-    prep = time.perf_counter() - t0
     ctx = _lib.Context.get(local)
+    dp = None
+    if args.pixels:
+        from neoloopfinder_b200.coolshim import PixelCooler
+        sub = SyntheticCooler(binsize=args.res, chromsizes={c: sizes[c] for c in names}, seed=404,
+                              amplitude=255.0 * args.res / 10000.0)
+        # same procedural pixels as `clr` needs the same global bin offsets: keep all names, fetch only mine
+        px = PixelCooler.from_cooler(_Only(sub, mine), band_bins=449, trans=False)
+        prep = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        dp = px.device_pixels(ctx, "sweight")
+        ctx.sync()
+        upload = time.perf_counter() - t1
+        ranges = [px.global_bins(c, 0, px._nbins(c)) for c in mine]
+    else:
+        for c in mine:
+            bw = clr.fetch_band(c, 450, "sweight")
+            g, kept = gap_free_band(bw)
+            bands.append(g)
+        prep = time.perf_counter() - t0
+        upload = 0.0
     forest = load_forest(MODEL, ctx)
     times, scored, loops_n = [], 0, 0
     prof = {}
@@ -72,8 +105,14 @@ def main():
             ctx.profile(True); ctx.profile_reset()
         ctx.sync(); t0 = time.perf_counter()
         b = ScoreBatch(4, 400, ctx)
+        nb = 0
         for g in bands:
             b.add_band(g)
+            nb += g.shape[0]
+        if dp is not None:
+            for lo, hi in ranges:
+                _job, kept = b.add_pixels(dp, lo, hi, balance=True)
+                nb += kept.size
         loops, (nc, ns, nd) = score_and_pool(b, forest, exp_arr, args.prob, args.res, 2, None, False)
         b.close(); ctx.sync()
         times.append(time.perf_counter() - t0)
@@ -90,7 +129,9 @@ def main():
         t = float(v.item()); scored = int(s[0].item()); loops_n = int(s[1].item())
     if rank == 0:
         print(json.dumps({"workload": "cfg4 genome-wide %d bp, %d chromosomes, banded input" % (args.res, len(names)),
-                          "n_gpus": world, "bins": int(sum(b.shape[0] for b in bands)) if world == 1 else None,
+                          "n_gpus": world, "bins": int(nb) if world == 1 else None,
+                          "input": "pixel table resident in HBM (gap removal + bands on the GPU)" if args.pixels else "host gap-free bands (H2D per pass)",
+                          "pixel_table": ({"nnz": int(px.count.size), "upload_s": round(upload, 4)} if args.pixels else None),
                           "scored_pixels": scored, "loops": loops_n, "seconds_per_pass": t,
                           "pixels_per_s": scored / t, "prep_seconds_rank0": prep, "pass_times": times,
                           "kernel_ms_last_pass_rank0": prof}))
