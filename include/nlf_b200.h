@@ -97,6 +97,9 @@ int nlf_assembly_create_from_pixels(nlf_ctx *ctx, nlf_pixels *px, int balance, c
                                     const int64_t *src_hi, const uint8_t *rev, int nblk,
                                     nlf_assembly **out);
 int nlf_assembly_size(nlf_assembly *a, int *n);
+/* Replace the per-bin vector whose pairwise products decide which pixels are valid (a pixel
+ * (x, y) counts when bias[x] * bias[y] > 0): Fusion.extract_bias keeps 1 / weight (callers.py:262-283). */
+int nlf_assembly_set_bias(nlf_assembly *a, const double *bias);
 /* complexSV.fusion_matrix (n x n) and complexSV.bias (n) back on the host; either may be NULL. */
 int nlf_assembly_fetch_matrix(nlf_assembly *a, double *M, double *bias);
 /* Fusion._extract_xy for every block pair j1<=j2 (pair index p = position in that nested
@@ -104,6 +107,13 @@ int nlf_assembly_fetch_matrix(nlf_assembly *a, double *M, double *bias);
  * diagonal i (numpy summation order) when at least mink are valid and the mean is > 0,
  * NaN otherwise; cnt_out = number of valid pixels. */
 int nlf_assembly_diag_means(nlf_assembly *a, int maxdiag, int mink, double *mean_out, int *cnt_out);
+/* The same for caller-chosen rectangles [row_lo,row_hi) x [col_lo,col_hi) of the matrix (they need
+ * not follow the block table): Fusion._extract_xy as Fusion.allele_slope uses it for the upstream,
+ * downstream and junction regions between up_i and down_i (callers.py:414-478).  Rectangle p
+ * fills mean_out / cnt_out[p*(maxdiag+1) ...]. */
+int nlf_assembly_rect_means(nlf_assembly *a, int nrect, const int *row_lo, const int *row_hi,
+                            const int *col_lo, const int *col_hi, int maxdiag, int mink,
+                            double *mean_out, int *cnt_out);
 /* assembly.py:536-549: op[j1*nblk+j2] 0 = keep, 1 = divide by val, 2 = multiply by val. */
 int nlf_assembly_set_scales(nlf_assembly *a, const int *op, const double *val);
 /* callers.py:504-522: kept_out[k] = original index of gap-free bin k; *n_kept = n'. */

@@ -51,11 +51,13 @@ _SIGNATURES = {
     "nlf_pixels_destroy": (C.c_int, [vp]),
     "nlf_assembly_create_from_pixels": (C.c_int, [vp, vp, C.c_int, i64p, i64p, u8p, C.c_int, C.POINTER(vp)]),
     "nlf_assembly_size": (C.c_int, [vp, ip]),
+    "nlf_assembly_set_bias": (C.c_int, [vp, dp]),
     "nlf_assembly_fetch_matrix": (C.c_int, [vp, dp, dp]),
     "nlf_expected_from_pixels": (C.c_int, [vp, vp, C.c_int, C.c_longlong, C.c_longlong, C.c_int, dp, llp]),
     "nlf_batch_add_pixels": (C.c_int, [vp, vp, C.c_int, C.c_longlong, C.c_longlong, ip, ip]),
     "nlf_assembly_create": (C.c_int, [vp, dp, C.c_int, dp, ip, ip, C.c_int, C.POINTER(vp)]),
     "nlf_assembly_diag_means": (C.c_int, [vp, C.c_int, C.c_int, dp, ip]),
+    "nlf_assembly_rect_means": (C.c_int, [vp, C.c_int, ip, ip, ip, ip, C.c_int, C.c_int, dp, ip]),
     "nlf_assembly_set_scales": (C.c_int, [vp, ip, dp]),
     "nlf_assembly_remove_gaps": (C.c_int, [vp, ip, ip]),
     "nlf_assembly_fetch_hcm": (C.c_int, [vp, dp]),

@@ -5,8 +5,9 @@ rearranged matrix, coordinate bookkeeping and the tiny per-block-pair regression
 (libnlf_b200): every pass over the n x n matrix -- masked per-diagonal means in numpy's summation
 order, the per-block rescale, the gap-column sums and the gap-free compaction.
 
-``assembleSV`` / ``filterSV`` / ``filterAssembly`` (graph assembly of SVs) belong to the upstream
-``assemble-complexSVs`` step and are out of scope here.
+``assembleSV`` / ``filterSV`` / ``filterAssembly`` (the inner loop of
+``assemble-complexSVs``, neoloop/assembly.py:12-275) reuse the same kernels: every SV and every candidate
+chain of SVs is tested by the distance decay of the contacts it induces.
 """
 from __future__ import annotations
 
@@ -20,9 +21,9 @@ from .util import find_chrom_pre
 
 log = logging.getLogger(__name__)
 
-__all__ = ["complexSV"]
+__all__ = ["complexSV", "assembleSV", "filterSV", "filterAssembly"]
 
-_MAXDIS_LADDER = (200000, 400000, 500000, 1000000, 1500000, 2000000)   # assembly.py:513
+from .callers import _MAXDIS_LADDER                       # assembly.py:513
 
 
 class complexSV(Fusion):
@@ -328,3 +329,174 @@ class complexSV(Fusion):
             key = (a[0], a[1], a[1] + res, b[0], b[1], b[1] + res)
             lines[key] = [(y - x) * res, 0 if self.chains[x] == self.chains[y] else 1]
         return lines
+
+
+# ----------------------------------------------------------------------------------------------
+# assemble-complexSVs: SV filter, SV graph, allele chains (neoloop/assembly.py:12-275)
+# ----------------------------------------------------------------------------------------------
+def filterSV(clr, c1, c2, p1, p2, s1, s2, note, span, col, protocol, cutoff, expected_values):
+    """One SV: keep it when the contacts across the junction decay like the global expected
+    (R^2 above ``cutoff``) and are strong enough relative to a flank; returns the graph node and the two
+    flanks trimmed to the detected bounds, or None (assembly.py:12-27)."""
+    from .util import map_coordinates
+    fu = Fusion(clr, c1, c2, p1, p2, s1, s2, note, span=span, col=col, protocol=protocol, trim=False,
+                expected_values=expected_values)
+    fu.detect_bounds()
+    fu.allele_slope()
+    fu.correct_heterozygosity()
+    if not (fu.m_g_r > cutoff and max(fu.u_s, fu.d_s) > 0.1):
+        return None
+    where = map_coordinates(fu.k_p, clr.binsize, c1, c2)[1]
+    up, down = where[fu.up_i], where[fu.down_i]
+    return [(c1, p1, s1, c2, p2, s2, note), (c1, up[1], fu.k_p[1]), (c2, fu.k_p[2], down[1])]
+
+
+def filterAssembly(clr, ID, span, col, path, protocol, expected):
+    """A chain of SVs is connectable when every block pair passes its regression and neighbouring
+    blocks are linked (assembly.py:29-36)."""
+    wk = complexSV(clr, ID, span, col, protocol=protocol, expected_values=expected)
+    wk.reorganize_matrix()
+    wk.correct_heterozygosity()
+    ok = (len(wk.pair_binary) == wk.valid_counts) and wk.connectivity
+    if wk._asm is not None:
+        wk._asm.close()
+    return ok, path
+
+
+def _flip(node):
+    """The same SV read from its other end."""
+    return node[3:6] + node[:3] + (node[-1],)
+
+
+class assembleSV(object):
+    """SV list -> filtered SVs -> directed graph of SVs whose flanks overlap -> maximal chains that
+    hold together in the contact map ("alleles") (assembly.py:39-275)."""
+
+    def __init__(self, clr, sv_fil, span=5000000, col='sweight', minIntra=500000,
+                 n_jobs=1, protocol='insitu', r_cutoff=0.6, expected_values=None):
+        from .util import load_translocation_fil
+        self.clr = clr
+        self.res = clr.binsize
+        self.protocol = protocol
+        self.span = span
+        self.balance_type = col
+        self.n_jobs = n_jobs
+        self.expected = expected_values
+        self.queue, self.lookup = [], {}
+        for c1, p1, s1, c2, p2, s2, note in load_translocation_fil(sv_fil, clr.binsize, minIntra):
+            rec = filterSV(clr, c1, c2, p1, p2, s1, s2, note, span, col, protocol, r_cutoff, expected_values)
+            if rec is not None:
+                self.queue.append(rec)
+                self.lookup[rec[0]] = [rec[1], rec[2]]
+
+    # -- graph ---------------------------------------------------------------------------------
+    def build_graph(self):
+        import networkx as nx
+        nodes = {}
+        for n, u, d in self.queue:
+            nodes[(n, u, d)] = n                 # as listed ...
+            nodes[(_flip(n), d, u)] = n          # ... and read from the other end
+        G = nx.DiGraph()
+        for a in nodes:
+            for b in nodes:
+                if nodes[a] == nodes[b]:
+                    continue
+                dis = self.connect(a, b)
+                if dis < np.inf:
+                    G.add_weighted_edges_from([(a, b, dis)])
+        self.graph = G
+        self.nodemap = nodes
+
+    def _check_overlap(self, i1, i2):
+        """(intersection / union, intersection) of two intervals (chrom, a, b) given in any order."""
+        if i1[0] != i2[0]:
+            return 0, 0
+        a0, a1 = sorted(i1[1:])
+        b0, b1 = sorted(i2[1:])
+        if a1 <= b0 or b1 <= a0:
+            return 0, 0
+        pts = sorted((a0, a1, b0, b1))
+        return (pts[2] - pts[1]) / (pts[3] - pts[0]), pts[2] - pts[1]
+
+    def connect(self, r1, r2):
+        """Edge weight r1 -> r2: the tail flank of r1 and the head flank of r2 must face each other
+        ('-' then '+', or '+' then '-'), overlap by more than four bins, and the two-SV chain must pass
+        filterAssembly; weight = union / intersection, else inf (assembly.py:190-223)."""
+        (n1, _u1, d1), (n2, u2, _d2) = r1, r2
+        if (n1[5] == '-') != (n2[2] == '+'):
+            return np.inf
+        o, itr = self._check_overlap(d1, u2)
+        if not (o > 0 and itr > 4 * self.res):
+            return np.inf
+        p = (r1, r2)
+        ok, _p = filterAssembly(self.clr, self._change_format(p), self.span, self.balance_type, p, self.protocol,
+                                self.expected)
+        return 1 / o if ok else np.inf
+
+    def _containloop(self, path):
+        """Pairs of non-adjacent flanks of a chain that overlap by more than 5 % (a chain that visits
+        the same region twice)."""
+        chain = [flank for p in path for flank in (p[1], p[2])]
+        hits = []
+        for i in range(len(chain)):
+            for j in range(i + 2, len(chain)):
+                if self._check_overlap(chain[i], chain[j])[0] > 0.05:
+                    hits.append((chain[i], chain[j]))
+        return hits
+
+    def _getreverse(self, path):
+        return [(_flip(n), d, u) for n, u, d in path[::-1]]
+
+    def _issubset(self, p1, p2):
+        """p1 occurs in p2 as a contiguous, equally ordered run."""
+        pos = []
+        for item in p1:
+            if item not in p2:
+                return False
+            pos.append(p2.index(item))
+        return bool(np.all(np.diff(np.r_[pos]) == 1))
+
+    def find_complexSV(self):
+        from networkx.algorithms import all_shortest_paths, has_path
+        pool = []
+        nodes = self.graph.nodes()
+        for n1 in nodes:
+            for n2 in nodes:
+                if n1 == n2 or not has_path(self.graph, n1, n2):
+                    continue
+                for p in all_shortest_paths(self.graph, n1, n2, weight=None):     # edge weights are not used
+                    if not self._containloop(p):
+                        pool.append((len(p), p))
+        pool.sort(reverse=True)
+        log.info('Filtering %d redundant candidates ...', len(pool))
+        held = [p for _len, p in pool
+                if filterAssembly(self.clr, self._change_format(p), self.span, self.balance_type, p, self.protocol,
+                                  self.expected)[0]]
+        alleles = []
+        for p in held:              # longest first: drop chains contained in a kept one, in either reading direction
+            if not any(self._issubset(p, v) or self._issubset(p, self._getreverse(v)) for v in alleles):
+                alleles.append(p)
+        self.alleles = alleles
+
+    # -- output ----------------------------------------------------------------------------------
+    def _change_format(self, path):
+        """Assembly line body: 'type,c1,p1,s1,c2,p2,s2' per SV, then the two outer bounds
+        (assembly.py:225-252)."""
+        names = [','.join(map(str, (p[0][-1],) + p[0][:-1])) for p in path]
+        b1, b2 = path[0][1], path[-1][2]
+        first = min(b1[1:]) if path[0][0][2] == '+' else max(b1[1:])
+        last = max(b2[1:]) if path[-1][0][5] == '-' else min(b2[1:])
+        return '\t'.join(names + ['%s,%s' % (b1[0], first), '%s,%s' % (b2[0], last)])
+
+    def print(self, complexSVs, outfil):
+        with open(outfil, 'w') as out:
+            for path in complexSVs:
+                out.write(self._change_format(path) + '\n')
+
+    def output_all(self, outfil):
+        with open(outfil, 'w') as out:
+            for i, path in enumerate(self.alleles):
+                out.write('A%d\t%s\n' % (i, self._change_format(path)))
+            for i, sv in enumerate(self.lookup):
+                path = [(sv, self.lookup[sv][0], self.lookup[sv][1])]
+                out.write('C%d\t%s\n' % (i, self._change_format(path)))

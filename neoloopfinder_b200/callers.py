@@ -6,8 +6,8 @@ reference; every pass over matrix data runs in the CUDA l
 the host: the per-block-pair regression (Spearman + isotonic + Huber on <= 400 points) and
 dictionary/coordinate bookkeeping.
 
-Not provided (off the neoloop-caller path): ``Fusion.get_matrix``,
-``detect_bounds``, ``allele_slope``, ``extract_bias`` (used only by assemble-complexSVs).
+``Fusion`` also carries the single-SV analysis of ``assemble-complexSVs``:
+``get_matrix``, ``extract_bias``, ``detect_bounds``, ``allele_slope``, ``correct_heterozygosity``.
 """
 from __future__ import annotations
 
@@ -90,8 +90,261 @@ def linear_regression_fit(exp1, exp2, min_samples=5):
     return rscores.max(), slopes[np.argmax(rscores)], warning
 
 
+_MAXDIS_LADDER = (200000, 400000, 500000, 1000000, 1500000, 2000000)   # callers.py:433, assembly.py:513
+
+
+def rearranged_matrix(clr, pieces, reversed_flags, balance, ctx=None):
+    """np.triu of the contact matrix of ``pieces`` [(chrom, start, end), ...] laid side by side, piece k
+    read 3'->5' when ``reversed_flags[k]`` (the construction shared by Fusion.get_matrix, callers.py:137-237,
+    and complexSV.reorganize_matrix, assembly.py:468-483).  With a resident pixel table the matrix is built
+    on the GPU and only the handle comes back: returns (M or None, DeviceAssembly or None, index)."""
+    index, start = [], 0
+    for r in pieces:
+        nbin = clr.bins().fetch(tuple(r))['chrom'].size
+        index.append((start, start + nbin))
+        start += nbin
+    n = start
+    if hasattr(clr, "device_pixels") and n > 0:
+        col = 'weight' if balance == False else balance       # noqa: E712 (bias column of the reference)
+        px = clr.device_pixels(ctx, col)
+        spans = [clr.global_bins(*clr._bin_extent(tuple(r))) for r in pieces]
+        asm = DeviceAssembly.from_pixels(px, [a for a, _b in spans], [b for _a, b in spans],
+                                         [bool(f) for f in reversed_flags], balance=bool(balance))
+        return None, asm, index
+    M = np.zeros((n, n))
+    for j1, (r1, f1, i1) in enumerate(zip(pieces, reversed_flags, index)):
+        for j2, (r2, f2, i2) in enumerate(zip(pieces, reversed_flags, index)):
+            if j1 > j2:
+                continue
+            sub = clr.matrix(balance=balance).fetch(tuple(r1), tuple(r2))
+            if f1:
+                sub = sub[::-1, :]
+            if f2:
+                sub = sub[:, ::-1]
+            M[i1[0]:i1[1], i2[0]:i2[1]] = sub
+    M = np.triu(M)
+    if balance:
+        M[np.isnan(M)] = 0
+    return M, None, index
+
+
 class Fusion(object):
-    """The part of the reference's ``Fusion`` that the neoloop-caller path inherits."""
+    """One SV breakpoint pair: the rearranged matrix of its two flanks, the induced-contact bounds and
+    the distance-decay slopes against the global expected (neoloop/callers.py:92-522).
+    ``assemble-complexSVs`` filters SVs with it (neoloop/assembly.py:12-27); ``complexSV`` inherits the
+    regression and gap-removal parts.  Matrix passes (the masked per-diagonal means of ``_extract_xy``)
+    run on the GPU; PCA / regression on at most a few hundred points stay on the host."""
+
+    def __init__(self, clr, c1, c2, p1, p2, s1, s2, sv_type, span=5000000,
+                 col='sweight', trim=True, protocol='insitu', expected_values=None):
+        from .util import find_chrom_pre
+        self.clr = clr
+        self.p1, self.p2, self.s1, self.s2 = p1, p2, s1, s2
+        self.res = clr.binsize
+        pre = find_chrom_pre(list(clr.chromnames))
+        self.c1 = pre + c1.lstrip('chr')
+        self.c2 = pre + c2.lstrip('chr')
+        self.chromsize1 = int(clr.chromsizes[self.c1])
+        self.chromsize2 = int(clr.chromsizes[self.c2])
+        self.balance_type = col
+        self.protocol = protocol
+        self.name = ','.join(map(str, [sv_type, c1.lstrip('chr'), p1, s1, c2.lstrip('chr'), p2, s2]))
+        self._asm = None
+        self._fusion_matrix = None
+        self._hcm = None
+        self.get_matrix(span, col, trim)
+        if expected_values is None:
+            self.load_expected()
+        else:
+            self.expected = expected_values
+
+    # ------------------------------------------------------------------ geometry + matrix
+    def _flanks(self, span, trim):
+        """(k_p, pieces, reversed flags): '+' at breakpoint 1 keeps the side left of it, '-' at breakpoint 2
+        the side right of it; the other two cases are read backwards.  Intra-chromosomal inversions and
+        '-+' pairs stop halfway between the breakpoints (callers.py:146-214)."""
+        res = self.res
+        b1, b2, r = self.p1 // res, self.p2 // res, span // res
+        intra = self.c1 == self.c2
+        half = int((b2 - b1) / 2)
+        if self.s1 == '+':
+            lo1, hi1 = max(b1 - r, 0) * res, min(b1 * res + res, self.chromsize1)
+        else:
+            lo1 = b1 * res
+            if intra and self.s2 == '-':
+                hi1 = min((b1 + r + 1) * res, (b2 - half) * res if trim else b2 * res - res)
+            elif intra:
+                hi1 = min(b1 + r + 1, b2 - half - 1) * res
+            else:
+                hi1 = min((b1 + r + 1) * res, self.chromsize1)
+        if self.s2 == '-':
+            lo2, hi2 = b2 * res, min((b2 + r + 1) * res, self.chromsize2)
+        else:
+            hi2 = min(b2 * res + res, self.chromsize2)
+            if intra and self.s1 == '+':
+                lo2 = max(b2 - r, (b1 + half) if trim else (b1 + 1)) * res
+            elif intra:
+                lo2 = max(b2 - r, b1 + half + 1) * res
+            else:
+                lo2 = max(b2 - r, 0) * res
+        rev = [self.s1 == '-', self.s2 == '+']
+        k_p = ([hi1, lo1] if rev[0] else [lo1, hi1]) + ([hi2, lo2] if rev[1] else [lo2, hi2])
+        return k_p, [(self.c1, lo1, hi1), (self.c2, lo2, hi2)], rev
+
+    def get_matrix(self, span, col, trim):
+        self.k_p, pieces, rev = self._flanks(span, trim)
+        self._pieces, self._rev = pieces, rev
+        M, asm, index = rearranged_matrix(self.clr, pieces, rev, col, getattr(self, '_ctx', None))
+        self._fusion_matrix, self._asm, self._index = M, asm, index
+        self._n_bins = index[-1][1]
+        self.fusion_point = index[0][1]
+
+    @property
+    def fusion_matrix(self):
+        if self._fusion_matrix is None and self._asm is not None:
+            self._fusion_matrix = self._asm.fusion_matrix()
+        return self._fusion_matrix
+
+    @fusion_matrix.setter
+    def fusion_matrix(self, M):
+        self._fusion_matrix = M
+
+    def _device_assembly(self) -> DeviceAssembly:
+        if self._asm is None:
+            self._asm = DeviceAssembly(self.fusion_matrix, np.zeros(self._n_bins), self._index, getattr(self, '_ctx', None))
+        return self._asm
+
+    def extract_bias(self, col='sweight'):
+        """1 / weight per bin of the rearranged axis, 0 where the weight is 0 or NaN (callers.py:240-262)."""
+        if col is False or col is None:
+            col = 'weight'
+        parts = []
+        for r, f in zip(self._pieces, self._rev):
+            t = np.asarray(self.clr.bins().fetch(tuple(r))[col].values, dtype=np.float64)
+            if f:
+                t = t[::-1]
+            ok = ~((t == 0) | np.isnan(t))
+            w = np.zeros_like(t)
+            w[ok] = 1 / t[ok]
+            parts.append(w)
+        self.bias = np.concatenate(parts)
+
+    # ------------------------------------------------------------------ induced-contact bounds
+    def detect_bounds(self):
+        """First principal component of the smoothed row / column correlation of the junction block
+        locates where the induced contacts stop on either side (callers.py:265-312)."""
+        from scipy.ndimage import gaussian_filter
+        from sklearn.decomposition import PCA
+        n, junc = self._n_bins, self.fusion_point
+        self.up_i, self.down_i = 0, n - 1
+        self.up_var_ratio = self.down_var_ratio = 0
+        inter = self.fusion_matrix[:junc, junc:]
+        rows, cols = inter.sum(axis=1) != 0, inter.sum(axis=0) != 0
+        if rows.sum() < 10 or cols.sum() < 10:
+            return
+        block = inter[rows][:, cols]
+        for upstream in (True, False):
+            corr = gaussian_filter(np.corrcoef(block, rowvar=upstream), sigma=1)
+            try:
+                pca = PCA(n_components=3, whiten=True)
+                pc1 = pca.fit_transform(corr)[:, 0]
+                ratio = pca.explained_variance_ratio_[0]
+                loc = self.locate(pc1, left_most=not upstream)
+                if upstream:
+                    self.up_i, self.up_var_ratio = np.where(rows)[0][loc], ratio
+                else:
+                    self.down_i, self.down_var_ratio = np.where(cols)[0][loc] + junc, ratio
+            except Exception:     # noqa: BLE001 - the reference falls back to the full flank on any failure
+                if upstream:
+                    self.up_i, self.up_var_ratio = 0, 0
+                else:
+                    self.down_i, self.down_var_ratio = n - 1, 0
+
+    def extend_stretches(self, arr, min_seed_len=2, max_gap=1, min_stripe_len=5):
+        """Runs of consecutive indices (>= min_seed_len long), joined across gaps of at most max_gap,
+        reported as [first, last + 1] when they span min_stripe_len (callers.py:315-333)."""
+        arr = np.sort(arr)
+        runs = [p for p in np.split(arr, np.where(np.diff(arr) != 1)[0] + 1) if len(p) >= min_seed_len]
+        out = []
+        cur_lo, cur_hi = runs[0][0], runs[0][-1]          # IndexError when nothing qualifies, as in the reference
+
+        def flush():
+            if cur_hi - cur_lo + 1 >= min_stripe_len:
+                out.append([cur_lo, cur_hi + 1])
+        for p in runs[1:]:
+            if p[0] - cur_hi < max_gap + 2:
+                cur_hi = p[-1]
+            else:
+                flush()
+                cur_lo, cur_hi = p[0], p[-1]
+        flush()
+        return out
+
+    def locate(self, pca1, left_most=True):
+        loci = self.extend_stretches(np.where(pca1 >= 0)[0]) + self.extend_stretches(np.where(pca1 <= 0)[0])
+        loci.sort()
+        return loci[0][1] - 1 if left_most else loci[-1][0]
+
+    # ------------------------------------------------------------------ slopes
+    def _region_means(self, up_i, down_i):
+        """Masked per-diagonal means (Fusion._extract_xy, callers.py:348-367) of the upstream, downstream
+        and junction regions, up to 2 Mb: one kernel launch for the three of them."""
+        junc = self.fusion_point
+        rects = [(up_i, junc, up_i, junc), (junc, down_i, junc, down_i), (up_i, junc, junc, down_i)]
+        maxdiag = _MAXDIS_LADDER[-1] // self.res
+        mean, _cnt = self._device_assembly().rect_means(rects, maxdiag, mink=3)
+        return mean
+
+    def allele_slope(self):
+        """Best Huber fit of local vs global expected over six distance cut-offs for the three regions, first
+        between the detected bounds, then -- unless all three fits are good -- over the whole flanks
+        (callers.py:415-478).  The six cut-offs are prefixes of one per-diagonal table."""
+        self.extract_bias(col=self.balance_type)
+        asm = self._device_assembly()
+        asm.set_bias(self.bias)
+        res = self.res
+        for up_i, down_i in ((self.up_i, self.down_i), (0, self.bias.size - 1)):
+            mean = self._region_means(int(up_i), int(down_i))
+            best = []
+            for row in mean:
+                kept = np.where(~np.isnan(row))[0]
+                memo, rs, ss = {}, [], []
+                for maxdis in _MAXDIS_LADDER:
+                    upto = kept[kept <= maxdis // res]
+                    if len(upto) not in memo:
+                        memo[len(upto)] = self.linear_regression({int(i): row[i] for i in upto}, self.expected)
+                    r, s, _w = memo[len(upto)]
+                    rs.append(r)
+                    ss.append(s)
+                rs = np.r_[rs]
+                best.append((rs.max(), ss[rs.argmax()]))
+            (self.u_g_r, self.u_g_s), (self.d_g_r, self.d_g_s), (self.m_g_r, self.m_g_s) = best
+            if self.u_g_r > 0.6 and self.d_g_r > 0.6 and self.m_g_r > 0.6 and self.m_g_s > 0:
+                break
+
+    def correct_heterozygosity(self):
+        """Relative slopes of the junction against each flank; ``hcm`` (the rescaled matrix,
+        callers.py:482-502) is materialised when the attribute is read."""
+        self.u_s = self.d_s = 0
+        self._hcm = None
+        if self.u_g_r > 0.6 and self.d_g_r > 0.6:
+            self.u_s = self.m_g_s / self.u_g_s
+            self.d_s = self.m_g_s / self.d_g_s
+
+    @property
+    def hcm(self):
+        if self._hcm is None:
+            junc = self.fusion_point
+            h = self.fusion_matrix.copy()
+            if self.u_g_r > 0.6 and self.d_g_r > 0.6:
+                slope, ms = max(self.u_g_s, self.d_g_s), min(self.u_g_s, self.d_g_s)
+                h[:junc, :junc] = h[:junc, :junc] / slope
+                h[junc:, junc:] = h[junc:, junc:] / slope
+                if self.m_g_r > 0.6 and self.m_g_s / ms > 0.1:
+                    box = (slice(self.up_i, junc), slice(junc, self.down_i))
+                    h[box] = h[box] * min(1 / self.m_g_s, 5 / slope)
+            self._hcm = h
+        return self._hcm
 
     def load_expected(self):
         """Bundled GM12878 in-situ expected tables (neoloop/callers.py:120-134)."""
@@ -109,8 +362,16 @@ class Fusion(object):
 
     def remove_gaps(self):
         """Gap-free matrix and gap-free -> original index map (neoloop/callers.py:504-522).
-        The column sums and the compaction run on the GPU; ``gap_free`` is materialised on the
-        host only if somebody reads the attribute."""
+        For an assembly (complexSV) the column scan and the compaction run on the GPU and ``gap_free`` is
+        materialised on the host only if somebody reads the attribute; a plain Fusion works on its ``hcm``."""
+        if getattr(self, "_scale_plan", None) is None and not hasattr(self, "blocks"):
+            h = self.hcm
+            keep = np.where(~(h.sum(axis=0) == 0))[0]
+            if 5 * 2 + 1 > keep.size:
+                keep = np.arange(h.shape[0])
+            self.index_map = dict(zip(np.arange(len(keep)), keep.astype(np.int64)))
+            self._gap_free = h[np.ix_(keep, keep)]
+            return
         asm = self._device_assembly()
         kept = asm.kept_index()
         self.index_map = dict(zip(np.arange(len(kept)), kept.astype(np.int64)))

@@ -244,6 +244,15 @@ NLF_EXPORT int nlf_assembly_create_from_pixels(nlf_ctx *ctx, nlf_pixels *px, int
     return NLF_OK;
 }
 
+// replace the per-bin validity vector (Fusion.extract_bias keeps 1 / weight, callers.py:262-283)
+NLF_EXPORT int nlf_assembly_set_bias(nlf_assembly *a, const double *bias)
+{
+    if (!a || !bias) return fail(NLF_ERR_ARG, "nlf_assembly_set_bias: NULL argument");
+    NLF_CUDA(cudaSetDevice(a->ctx->device));
+    NLF_CUDA(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * a->n, cudaMemcpyHostToDevice, a->ctx->stream));
+    return NLF_OK;
+}
+
 NLF_EXPORT int nlf_assembly_size(nlf_assembly *a, int *n)
 {
     if (!a || !n) return fail(NLF_ERR_ARG, "nlf_assembly_size: NULL argument");
@@ -263,36 +272,35 @@ NLF_EXPORT int nlf_assembly_fetch_matrix(nlf_assembly *a, double *M, double *bia
     return NLF_OK;
 }
 
-NLF_EXPORT int nlf_assembly_diag_means(nlf_assembly *a, int maxdiag, int mink, double *mean_out, int *cnt_out)
+// masked per-diagonal means of arbitrary rectangles [lo1,hi1) x [lo2,hi2) of the fusion matrix
+static int rect_means(nlf_assembly *a, int nrect, const int *lo1, const int *hi1, const int *lo2, const int *hi2,
+                      int maxdiag, int mink, double *mean_out, int *cnt_out)
 {
-    if (!a || maxdiag < 0 || !mean_out || !cnt_out) return fail(NLF_ERR_ARG, "nlf_assembly_diag_means: bad arguments");
     nlf_ctx *c = a->ctx;
     NLF_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    const int nb = a->nblk, npairs = nb * (nb + 1) / 2, nd = maxdiag + 1;
-    std::vector<int> lo1, hi1, lo2, hi2;
+    const int nd = maxdiag + 1;
     int maxlen = 1;
-    for (int j1 = 0; j1 < nb; j1++)
-        for (int j2 = j1; j2 < nb; j2++) {
-            lo1.push_back(a->blo[j1]); hi1.push_back(a->bhi[j1]);
-            lo2.push_back(a->blo[j2]); hi2.push_back(a->bhi[j2]);
-            maxlen = std::max(maxlen, a->bhi[j1] - a->blo[j1]);
-        }
-    const int total = npairs * nd;
+    for (int p = 0; p < nrect; p++) {
+        if (lo1[p] < 0 || hi1[p] > a->n || lo2[p] < 0 || hi2[p] > a->n)
+            return fail(NLF_ERR_ARG, "rectangle %d [%d,%d) x [%d,%d) outside the %d-bin matrix", p, lo1[p], hi1[p], lo2[p], hi2[p], a->n);
+        maxlen = std::max(maxlen, hi1[p] - lo1[p]);
+    }
+    const int total = nrect * nd;
     int *d_par, *d_cnt;
     double *d_scratch, *d_mean;
-    NLF_CUDA(cudaMallocAsync(&d_par, sizeof(int) * 4 * npairs, s));
+    NLF_CUDA(cudaMallocAsync(&d_par, sizeof(int) * 4 * nrect, s));
     NLF_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * total, s));
     NLF_CUDA(cudaMallocAsync(&d_mean, sizeof(double) * total, s));
     NLF_CUDA(cudaMallocAsync(&d_scratch, sizeof(double) * (size_t)total * maxlen, s));
-    NLF_CUDA(cudaMemcpyAsync(d_par, lo1.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(d_par + npairs, hi1.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(d_par + 2 * npairs, lo2.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(d_par + 3 * npairs, hi2.data(), sizeof(int) * npairs, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par, lo1, sizeof(int) * nrect, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par + nrect, hi1, sizeof(int) * nrect, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par + 2 * nrect, lo2, sizeof(int) * nrect, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_par + 3 * nrect, hi2, sizeof(int) * nrect, cudaMemcpyHostToDevice, s));
     {
         KLaunch k(c, P_NORM);
-        k_pair_diag_means<<<(total + 7) / 8, 256, 0, s>>>(a->d_M, a->n, a->d_bias, d_par, d_par + npairs, d_par + 2 * npairs,
-                                                          d_par + 3 * npairs, npairs, maxdiag, mink, d_scratch, maxlen,
+        k_pair_diag_means<<<(total + 7) / 8, 256, 0, s>>>(a->d_M, a->n, a->d_bias, d_par, d_par + nrect, d_par + 2 * nrect,
+                                                          d_par + 3 * nrect, nrect, maxdiag, mink, d_scratch, maxlen,
                                                           d_cnt, d_mean);
     }
     NLF_CUDA(cudaGetLastError());
@@ -304,6 +312,30 @@ NLF_EXPORT int nlf_assembly_diag_means(nlf_assembly *a, int maxdiag, int mink, d
     NLF_CUDA(cudaFreeAsync(d_mean, s));
     NLF_CUDA(cudaFreeAsync(d_scratch, s));
     return NLF_OK;
+}
+
+NLF_EXPORT int nlf_assembly_diag_means(nlf_assembly *a, int maxdiag, int mink, double *mean_out, int *cnt_out)
+{
+    if (!a || maxdiag < 0 || !mean_out || !cnt_out) return fail(NLF_ERR_ARG, "nlf_assembly_diag_means: bad arguments");
+    const int nb = a->nblk;
+    std::vector<int> lo1, hi1, lo2, hi2;
+    for (int j1 = 0; j1 < nb; j1++)
+        for (int j2 = j1; j2 < nb; j2++) {
+            lo1.push_back(a->blo[j1]); hi1.push_back(a->bhi[j1]);
+            lo2.push_back(a->blo[j2]); hi2.push_back(a->bhi[j2]);
+        }
+    return rect_means(a, (int)lo1.size(), lo1.data(), hi1.data(), lo2.data(), hi2.data(), maxdiag, mink, mean_out, cnt_out);
+}
+
+// Fusion._extract_xy for caller-chosen rectangles (Fusion.allele_slope, callers.py:414-478: the
+// upstream / downstream / junction regions bounded by up_i and down_i)
+NLF_EXPORT int nlf_assembly_rect_means(nlf_assembly *a, int nrect, const int *row_lo, const int *row_hi,
+                                       const int *col_lo, const int *col_hi, int maxdiag, int mink,
+                                       double *mean_out, int *cnt_out)
+{
+    if (!a || nrect <= 0 || !row_lo || !row_hi || !col_lo || !col_hi || maxdiag < 0 || !mean_out || !cnt_out)
+        return fail(NLF_ERR_ARG, "nlf_assembly_rect_means: bad arguments");
+    return rect_means(a, nrect, row_lo, row_hi, col_lo, col_hi, maxdiag, mink, mean_out, cnt_out);
 }
 
 NLF_EXPORT int nlf_assembly_set_scales(nlf_assembly *a, const int *op, const double *val)

@@ -127,6 +127,25 @@ class DeviceAssembly:
                                                   ptr(cnt, C.c_int)))
         return mean, cnt
 
+    def set_bias(self, bias):
+        b = f64(bias)
+        if b.size != self.n:
+            raise ValueError("bias vector must have one entry per bin")
+        check(_lib.load().nlf_assembly_set_bias(self.h, ptr(b, C.c_double)))
+        self.ctx.sync()
+
+    def rect_means(self, rects, maxdiag: int, mink: int = 3):
+        """Fusion._extract_xy for rectangles [(row_lo, row_hi, col_lo, col_hi), ...] of the matrix:
+        -> (mean[nrect, maxdiag+1] with NaN where not kept, count[nrect, maxdiag+1])."""
+        r = np.asarray(rects, dtype=np.int64).reshape(-1, 4)
+        cols = [i32(r[:, k]) for k in range(4)]
+        mean = np.empty((len(r), maxdiag + 1), dtype=np.float64)
+        cnt = np.empty((len(r), maxdiag + 1), dtype=np.int32)
+        check(_lib.load().nlf_assembly_rect_means(self.h, len(r), ptr(cols[0], C.c_int), ptr(cols[1], C.c_int),
+                                                  ptr(cols[2], C.c_int), ptr(cols[3], C.c_int), int(maxdiag), int(mink),
+                                                  ptr(mean, C.c_double), ptr(cnt, C.c_int)))
+        return mean, cnt
+
     def set_scales(self, op, val):
         op = i32(op).reshape(self.nblk, self.nblk)
         val = f64(val).reshape(self.nblk, self.nblk)

@@ -104,6 +104,55 @@ def calculate_expected(clr, chroms, maxdis=5000000, balance=True, nproc=1) -> Di
     return dict(zip(d, fit.predict(d)))
 
 
+def load_translocation_fil(fil_path, res, minIntra):
+    """SV list of ``assemble-complexSVs`` (neoloop/util.py:65-101): lines ``chrA chrB ++|+-|-+|-- posA posB type``;
+    a position may be an interval ``s-e`` no wider than one bin (its midpoint is used).  Intra-chromosomal pairs
+    are ordered by position, dropped below ``minIntra`` (duplications, '-+', below twice that).  Returns the
+    sorted unique records (c1, p1, s1, c2, p2, s2, type) with the ``chr`` prefix stripped."""
+    def position(field):
+        if '-' not in field:
+            return int(field)
+        s, e = (int(v) for v in field.split('-'))
+        return None if e - s > res else (s + e) // 2
+
+    records = set()
+    with open(fil_path) as source:
+        for line in source:
+            c1, c2, strands, f1, f2, note = line.rstrip().split()
+            p1, p2 = position(f1), position(f2)
+            if p1 is None or p2 is None:
+                continue
+            s1, s2 = strands[0], strands[1]
+            if c1 == c2:
+                if abs(p2 - p1) < minIntra:
+                    continue
+                if p1 > p2:
+                    p1, p2, s1, s2 = p2, p1, s2, s1
+                if s1 == '-' and s2 == '+' and abs(p2 - p1) < minIntra * 2:
+                    continue
+            records.add((c1.lstrip('chr'), p1, s1, c2.lstrip('chr'), p2, s2, note))
+    return sorted(records)
+
+
+def map_coordinates(k_p, res, chrom_1, chrom_2, unit='bp'):
+    """(forward, reverse) maps between (chrom, bin start) and the bin index on the rearranged axis of a
+    Fusion matrix described by ``k_p`` (neoloop/util.py:335-389): a side given as (high, low) is read backwards."""
+    def side(a, b, first):
+        lo, hi = (a, b) if a < b else (b, a)
+        lo_bin, hi_bin = lo // res, -(-hi // res)
+        nbin = hi_bin - lo_bin
+        keys = range(lo, hi, res) if unit == 'bp' else range(lo_bin, hi_bin)
+        idx = range(first, first + nbin) if a < b else range(first + nbin - 1, first - 1, -1)
+        return dict(zip(keys, idx)), nbin
+
+    d1, n1 = side(k_p[0], k_p[1], 0)
+    d2, _n2 = side(k_p[2], k_p[3], n1)
+    forward = {(chrom_1, k): v for k, v in d1.items()}
+    forward.update({(chrom_2, k): v for k, v in d2.items()})
+    reverse = {v: k for k, v in forward.items()}
+    return forward, reverse
+
+
 def image_normalize(arr_2d):
     """(a - min) / (max - min) (neoloop/util.py:493-497).  On the scoring path this runs inside
     the CUDA feature kernel; this helper exists for API compatibility on small host arrays."""
