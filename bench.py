@@ -34,13 +34,28 @@ RES = 10000
 SPAN = 3_000_000
 N_ASSEMBLIES = 50
 THRESHOLD = 0.9
+KIND = "simple"             # synth.make_workload kind: 'simple' (cfg2) or 'complex' (cfg3)
+WORKLOAD = "cfg2"
 MODEL = os.path.join(ROOT, "tests", "golden", "forest_w6.joblib")
 
 
+def select_workload(name, n_assemblies):
+    """cfg2 (default, BASELINE.json configs[1]): 10 kb, simple SV assemblies.  cfg3 (configs[2]): 5 kb, complex
+    multi-breakpoint assemblies (2-5 chained SVs, 3-6 blocks, 1.2-4 k bins each); fewer of them per GPU because
+    the untimed host preparation fetches every block pair from the procedural map."""
+    global RES, KIND, WORKLOAD, N_ASSEMBLIES
+    WORKLOAD = name
+    if name == "cfg3":
+        RES, KIND = 5000, "complex"
+    N_ASSEMBLIES = n_assemblies if n_assemblies else (24 if name == "cfg3" else 50)
+    return N_ASSEMBLIES
+
+
 def workload_config(n_gpus):
+    what = ("cfg2: synthetic 10 kb hg38-sized map, %d simple SV assemblies per GPU" if WORKLOAD == "cfg2" else
+            "cfg3: synthetic 5 kb hg38-sized map, %d complex (2-5 chained SVs) assemblies per GPU") % N_ASSEMBLIES
     return {
-        "workload": "cfg2: synthetic 10 kb hg38-sized map, %d simple SV assemblies per GPU, 3 Mb span, prob %.2f"
-                    % (N_ASSEMBLIES, THRESHOLD),
+        "workload": "%s, 3 Mb span, prob %.2f" % (what, THRESHOLD),
         "resolution": RES, "assemblies_per_gpu": N_ASSEMBLIES, "span_bp": SPAN,
         "forest": "synthetic sklearn RandomForest, 100 trees, depth<=20, 32048 nodes, 169 features (tests/golden/forest_w6.joblib)",
         "expected": "analytic A/(d+1) of the procedural map",
@@ -52,7 +67,7 @@ def workload_config(n_gpus):
 # --------------------------------------------------------------------------------------------
 def build_assemblies(rank, n_asm):
     from neoloopfinder_b200.synth import analytic_expected, make_workload
-    clr, lines = make_workload("simple", res=RES, seed=100 + rank, n_assemblies=n_asm, span=SPAN)
+    clr, lines = make_workload(KIND, res=RES, seed=100 + rank, n_assemblies=n_asm, span=SPAN)
     expected = analytic_expected(clr)
     return clr, lines, expected
 
@@ -232,9 +247,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--assemblies", type=int, default=N_ASSEMBLIES)
+    ap.add_argument("--assemblies", type=int, default=0, help="assemblies per GPU (default: 50 for cfg2, 24 for cfg3)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.assemblies = select_workload(args.workload, args.assemblies)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -375,7 +392,7 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tr.get("assemblies") == args.assemblies and tr.get("kernel") == "k_features":
+            if WORKLOAD == "cfg2" and tr.get("assemblies") == args.assemblies and tr.get("kernel") == "k_features":
                 traffic = tr["dram_bytes_per_launch"]
         except (OSError, ValueError, KeyError):
             pass
