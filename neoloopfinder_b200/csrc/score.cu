@@ -283,11 +283,11 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 //   phase 2  per matrix row x: axis-0 gaussian pass shared by the 32 windows of the row,
 //            then per window row the axis-1 pass, min/max, normalise, cast to float32.
 // =============================================================================================
-template <int W>
+template <int W, int TXP>
 struct FeatCfg {
     static constexpr int S = 2 * W + 1;
     static constexpr int F = S * S;
-    static constexpr int TX = (W >= 7) ? 8 : 16;   // matrix rows per tile (static shared memory stays below 48 KB)
+    static constexpr int TX = TXP;              // matrix rows per tile
     static constexpr int TR = TX + 2 * W;       // tile rows incl. halo
     static constexpr int TC = 32 + 4 * W;       // tile band columns incl. halo
     static constexpr int VC = 32 + 2 * W;       // columns of the axis-0 result
@@ -301,18 +301,22 @@ __device__ __forceinline__ int reflect_idx(int i, int n)
     return i;
 }
 
-template <int W>
-__global__ void __launch_bounds__(FeatCfg<W>::NT, 2)
+template <int W, int TXP>
+__global__ void __launch_bounds__(FeatCfg<W, TXP>::NT, 2)
 k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int tile_offset,
            int lower, int upper, int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, PixRef *__restrict__ pix,
            float *__restrict__ featT, unsigned *__restrict__ slot_counter, unsigned max_slots,
            int *__restrict__ overflow, unsigned *__restrict__ nanmask)
 {
-    using C = FeatCfg<W>;
+    using C = FeatCfg<W, TXP>;
     constexpr int S = C::S, F = C::F, TX = C::TX, TR = C::TR, TC = C::TC, VC = C::VC, NT = C::NT;
-    __shared__ double Rt[TR][TC];
-    __shared__ double Et[TR][TC];
-    __shared__ unsigned char Hs[TR][TC];
+    static_assert(TC <= 64, "one 64-bit non-zero mask per tile row");
+    // raw and observed/expected tile: dynamic shared memory (2 * TR * TC doubles; above 48 KB per CTA in
+    // total for the taller tiles, see launch_features)
+    extern __shared__ __align__(16) double feat_dyn[];
+    double (*Rt)[TC] = reinterpret_cast<double (*)[TC]>(feat_dyn);
+    double (*Et)[TC] = reinterpret_cast<double (*)[TC]>(feat_dyn + TR * TC);
+    __shared__ unsigned long long nzmask[TR];     // bit cc of row rr: Rt[rr][cc] != 0
     __shared__ double Vx[S][VC];
     __shared__ double2 red_mm[2][S][32];      // {row min, row max}, double buffered
     __shared__ double fin_mn[2][32], fin_den[2][32], fin_rden[2][32];   // window min, max - min, 1 / (max - min)
@@ -353,14 +357,12 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
         Et[rr][cc] = (ad < nexp) ? __ddiv_rn(v, expv[ad]) : v;
     }
     __syncthreads();
-    for (int k = tid; k < TR * TC; k += NT) {
-        int rr = k / TC, cc = k % TC;
-        int c = 0;
-        if (cc + 2 * W < TC) {
-#pragma unroll
-            for (int b = 0; b < S; b++) c += (Rt[rr][cc + b] != 0.0);
-        }
-        Hs[rr][cc] = (unsigned char)c;
+    // one 64-bit mask of the non-zero cells per tile row (two ballots); count_nonzero of any window row is
+    // then a shift, a mask and a popcount
+    for (int rr = warp; rr < TR; rr += S) {
+        const unsigned lo = __ballot_sync(0xffffffffu, Rt[rr][lane] != 0.0);
+        const unsigned hi = __ballot_sync(0xffffffffu, (lane + 32 < TC) && Rt[rr][(lane + 32 < TC) ? lane + 32 : 0] != 0.0);
+        if (lane == 0) nzmask[rr] = ((unsigned long long)hi << 32) | lo;
     }
     __syncthreads();
 
@@ -378,7 +380,8 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
         if (ok) {
             int nz = 0;
 #pragma unroll
-            for (int a = 0; a < S; a++) nz += Hs[xi + a][lane + 2 * W - a];
+            for (int a = 0; a < S; a++)
+                nz += __popcll((nzmask[xi + a] >> (lane + 2 * W - a)) & ((1ull << S) - 1ull));
             ok = !((double)nz < (double)F * 0.1);
         }
         if (ok) {
@@ -1274,7 +1277,7 @@ struct HostJob {
 struct nlf_batch {
     nlf_ctx *ctx = nullptr;
     int lower = 4, upper = 400, pitch = 416, bw = 414;
-    int W = 0, ndp = 0, ndt = 0;
+    int W = 0, ndp = 0, ndt = 0, TX = 16;
     bool keep_slots = false;
     std::vector<HostJob> jobs;
     cudaEvent_t ev_inputs = nullptr;         // recorded on the copy stream after the last uploaded input
@@ -1685,15 +1688,41 @@ NLF_EXPORT int nlf_batch_add_pixels(nlf_batch *b, nlf_pixels *px, int balance, l
 
 NLF_EXPORT int nlf_batch_njobs(nlf_batch *b) { return b ? (int)b->jobs.size() : 0; }
 
-template <int W>
-static int launch_features(nlf_batch *b, int tile_offset, int n_tiles, int nexp)
+// Matrix rows per feature tile.  Taller tiles amortise the per-tile prologue (band tile + halo load, O/E
+// division, gates, slot claim: ~29 % of the warp time at 16 rows in the ncu source view) over more rows.
+static int feat_tx(int w)
 {
+    int tx = (w >= 7) ? 16 : 32;
+    if (const char *e = getenv("NLF_FEAT_TX")) {
+        const int v = atoi(e);
+        if ((w >= 7 && (v == 8 || v == 16)) || (w < 7 && (v == 16 || v == 32))) tx = v;
+    }
+    return tx;
+}
+
+template <int W, int TXP>
+static int launch_features_tx(nlf_batch *b, int tile_offset, int n_tiles, int nexp)
+{
+    using C = FeatCfg<W, TXP>;
     nlf_ctx *c = b->ctx;
+    const size_t dyn = sizeof(double) * 2 * C::TR * C::TC;
+    static bool configured[64] = {false};
+    if (!configured[c->device & 63]) {
+        NLF_CUDA(cudaFuncSetAttribute(k_features<W, TXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        configured[c->device & 63] = true;
+    }
     KLaunch k(c, P_FEATURE);
-    k_features<W><<<n_tiles, FeatCfg<W>::NT, 0, c->stream>>>(
+    k_features<W, TXP><<<n_tiles, C::NT, dyn, c->stream>>>(
         b->d_jobs, b->d_tile_base, (int)b->jobs.size(), tile_offset, b->lower, b->upper, b->pitch, b->ndp, b->ndt,
         b->d_exp, nexp, b->d_pix, b->d_featT, b->d_group_counter, b->max_groups * 32u, b->d_overflow, b->d_nanmask);
     return NLF_OK;
+}
+
+static int launch_features(nlf_batch *b, int w, int tx, int tile_offset, int n_tiles, int nexp)
+{
+    if (w == 5) return tx == 32 ? launch_features_tx<5, 32>(b, tile_offset, n_tiles, nexp) : launch_features_tx<5, 16>(b, tile_offset, n_tiles, nexp);
+    if (w == 6) return tx == 32 ? launch_features_tx<6, 32>(b, tile_offset, n_tiles, nexp) : launch_features_tx<6, 16>(b, tile_offset, n_tiles, nexp);
+    return tx == 16 ? launch_features_tx<7, 16>(b, tile_offset, n_tiles, nexp) : launch_features_tx<7, 8>(b, tile_offset, n_tiles, nexp);
 }
 
 // dynamic shared memory of the cooperative forest kernels for a part of `nodes` nodes in `ntree` trees
@@ -1811,7 +1840,7 @@ static int upload_jobs(nlf_batch *b, int w)
 {
     nlf_ctx *c = b->ctx;
     const int nj = (int)b->jobs.size();
-    const int TX = (w >= 7) ? 8 : 16;                 // FeatCfg<W>::TX
+    const int TX = b->TX = feat_tx(w);               // FeatCfg<W, TX>::TX
     const int up1 = b->upper + 2;
     std::vector<JobDev> jd(nj);
     std::vector<int> tb(nj + 1);
@@ -1935,7 +1964,7 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     // (TX*32 slots of F floats per tile) stays below the budget, each chunk going through the feature
     // and the forest kernels before the next one starts (results land in `prob` by pixel coordinates).
     const int tiles = b->total_tiles;
-    const int TXh = (w >= 7) ? 8 : 16;
+    const int TXh = b->TX;
     size_t budget_mb = 12288;
     if (const char *e = getenv("NLF_FEATURE_BUDGET_MB")) budget_mb = (size_t)std::max(1, atoi(e));
     const size_t slot_bytes = (size_t)F * 4 + sizeof(PixRef) + 8;
@@ -1957,9 +1986,8 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
         const int t_cnt = (int)std::min<long long>(tiles_per_chunk, tiles - t_off);
         NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
         NLF_CUDA(cudaMemsetAsync(b->d_nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
-        if (w == 5) launch_features<5>(b, t_off, t_cnt, nexp);
-        else if (w == 6) launch_features<6>(b, t_off, t_cnt, nexp);
-        else launch_features<7>(b, t_off, t_cnt, nexp);
+        rc = launch_features(b, w, TXh, t_off, t_cnt, nexp);
+        if (rc) return rc;
         NLF_CUDA(cudaGetLastError());
         rc = launch_forest(b, f, w, F);
         if (rc) return rc;
