@@ -28,3 +28,24 @@ def test_call_resolution_same_on_one_and_two_gpus():
     assert len(merge_results(two)) > 0
     # the second device really worked: its context exists and launched kernels
     assert _lib.Context.get(1).launch_count() > 0
+
+
+def test_resident_pixel_table_on_two_gpus():
+    """Row f-2 across devices: every GPU holds its own copy of the pixel table (uploaded by the thread
+    that drives it); the merged calls equal the single-GPU and the cooler-surface results."""
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.cli import call_resolution
+    from neoloopfinder_b200.coolshim import PixelCooler, SyntheticCooler
+    from neoloopfinder_b200.synth import SMALL_CHROMSIZES, analytic_expected, make_workload
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    clr, lines = make_workload("simple", res=10000, seed=77, n_assemblies=8, chromsizes=SMALL_CHROMSIZES, span=1000000)
+    px = PixelCooler.from_cooler(clr)
+    expected = analytic_expected(clr)
+    model = os.path.join(GOLDEN, "forest_w6.joblib")
+    host = call_resolution(clr, lines, 1000000, "sweight", 0.5, 2, False, model, expected, devices=[0])
+    one = call_resolution(px, lines, 1000000, "sweight", 0.5, 2, False, model, expected, devices=[0])
+    two = call_resolution(px, lines, 1000000, "sweight", 0.5, 2, False, model, expected, devices=[0, 1])
+    assert host == one == two
+    assert sum(len(r) for r in two if r) > 0
+    assert len({k[1] for k in px._device}) == 2          # one resident copy per device
