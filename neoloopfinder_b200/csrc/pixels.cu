@@ -270,19 +270,22 @@ int nlf_pixels_fill_assembly(nlf_pixels *px, int balance, const long long *src_l
     B.out_lo = (const int *)(d_tab + sizeof(long long) * 2 * nblk);
     B.rev = d_tab + sizeof(long long) * 2 * nblk + sizeof(int) * nblk;
     B.nblk = nblk;
-    NLF_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * (size_t)n * n, s));
-    {
-        KLaunch k(c, P_NORM);
-        const long long warps = (long long)n * nblk;
-        k_px_assemble<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(px->d_off, px->d_bin2, px->d_cnt, px->d_w, balance, B,
-                                                                   d_blk, n, d_M);
+    cudaError_t e = cudaMemsetAsync(d_M, 0, sizeof(double) * (size_t)n * n, s);
+    if (e == cudaSuccess) {
+        {
+            KLaunch k(c, P_NORM);
+            const long long warps = (long long)n * nblk;
+            k_px_assemble<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(px->d_off, px->d_bin2, px->d_cnt, px->d_w, balance, B,
+                                                                       d_blk, n, d_M);
+        }
+        {
+            KLaunch k(c, P_NORM);
+            k_px_bias<<<(n + 127) / 128, 128, 0, s>>>(px->d_w, B, d_blk, n, d_bias);
+        }
+        e = cudaGetLastError();
     }
-    {
-        KLaunch k(c, P_NORM);
-        k_px_bias<<<(n + 127) / 128, 128, 0, s>>>(px->d_w, B, d_blk, n, d_bias);
-    }
-    NLF_CUDA(cudaGetLastError());
-    NLF_CUDA(cudaFreeAsync(d_tab, s));
+    cudaFreeAsync(d_tab, s);                       // stream ordered: after the kernels that read it
+    NLF_CUDA(e);
     return NLF_OK;
 }
 
@@ -337,18 +340,22 @@ int nlf_pixels_export_band(nlf_pixels *px, int balance, long long lo, long long 
     NLF_CUDA(cudaMallocAsync(&d_rank, sizeof(int) * n, s));
     NLF_CUDA(cudaMemcpyAsync(d_kept, kept.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, s));
     NLF_CUDA(cudaMemcpyAsync(d_rank, rank.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
-    double *band;
-    NLF_CUDA(c->big_alloc((void **)&band, sizeof(double) * (size_t)nk * pitch));
-    NLF_CUDA(cudaMemsetAsync(band, 0, sizeof(double) * (size_t)nk * pitch, s));
-    {
+    double *band = nullptr;
+    cudaError_t e = c->big_alloc((void **)&band, sizeof(double) * (size_t)nk * pitch);
+    if (e == cudaSuccess) e = cudaMemsetAsync(band, 0, sizeof(double) * (size_t)nk * pitch, s);
+    if (e == cudaSuccess) {
         KLaunch k(c, P_BANDIFY);
         k_px_gapband<<<(unsigned)((nk + 7) / 8), 256, 0, s>>>(px->d_off, px->d_bin2, px->d_cnt, px->d_w, balance, lo, hi,
                                                                d_kept, d_rank, nk, bw, pitch, band);
     }
-    NLF_CUDA(cudaGetLastError());
-    NLF_CUDA(cudaStreamSynchronize(s));            // rank / kept host vectors are read by the copies above
-    NLF_CUDA(cudaFreeAsync(d_kept, s));
-    NLF_CUDA(cudaFreeAsync(d_rank, s));
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);       // rank / kept host vectors are read by the copies above
+    cudaFreeAsync(d_kept, s);
+    cudaFreeAsync(d_rank, s);
+    if (e != cudaSuccess) {
+        if (band) c->big_free(band);
+        NLF_CUDA(e);
+    }
     *d_band_out = band;
     return NLF_OK;
 }
