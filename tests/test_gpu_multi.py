@@ -35,7 +35,7 @@ def test_resident_pixel_table_on_two_gpus():
     that drives it); the merged calls equal the single-GPU and the cooler-surface results."""
     from neoloopfinder_b200 import _lib
     from neoloopfinder_b200.cli import call_resolution
-    from neoloopfinder_b200.coolshim import PixelCooler, SyntheticCooler
+    from neoloopfinder_b200.coolshim import PixelCooler
     from neoloopfinder_b200.synth import SMALL_CHROMSIZES, analytic_expected, make_workload
     if _lib.device_count() < 2:
         pytest.skip("needs two GPUs")
