@@ -108,15 +108,24 @@ def gap_free_matrices_cpu(clr, lines, expected, limit):
     return out
 
 
+_CPU_CORES = {}      # per worker process: matrix -> (PeakachuPort, all candidate rows, all candidate columns)
+
+
 def _cpu_score_one(args):
     """The reference's scoring path (Peakachu init, candidates, getwindow, predict_proba, pooling)
-    on one gap-free matrix, restricted to one slice of its candidate list."""
+    on one gap-free matrix, restricted to one slice of its candidate list.  The per-matrix set-up
+    (CSR, candidates, model load: once per ~150 k candidates in the reference) is kept per worker
+    process, so short slices measure the same per-pixel rate as whole matrices."""
     G, index_map, chains, expected, model_path, lo, hi, thre = args
     from oracle import pyport
-    core = pyport.PeakachuPort(G, upper=400 * RES, res=RES)
-    core.load_expected(expected)
-    core.load_models(model_path)
-    core.ridx, core.cidx = core.ridx[lo:hi], core.cidx[lo:hi]
+    key = (G.shape[0], float(G[::5, ::5].sum()), model_path)
+    if key not in _CPU_CORES:
+        core = pyport.PeakachuPort(G, upper=400 * RES, res=RES)
+        core.load_expected(expected)
+        core.load_models(model_path)
+        _CPU_CORES[key] = (core, core.ridx, core.cidx)
+    core, ridx, cidx = _CPU_CORES[key]
+    core.ridx, core.cidx = ridx[lo:hi], cidx[lo:hi]
     cap = {}
     core.predict(thre=thre, no_pool=False, min_count=2, index_map=index_map, chains=chains, capture=cap)
     return int(cap.get("n_scored", 0))
@@ -125,21 +134,21 @@ def _cpu_score_one(args):
 CPU_SLICE = 50000      # candidates per work unit (about 13 s of one core)
 
 
-def cpu_work_units(items, expected, n_units):
+def cpu_work_units(items, expected, n_units, cpu_slice=CPU_SLICE):
     """(matrix, candidate slice) units: unit k takes slice k // n_items of matrix k % n_items."""
     units = []
     for k in range(n_units):
         G, im, ch = items[k % len(items)]
         s = k // len(items)
-        units.append((G, im, ch, expected, MODEL, s * CPU_SLICE, (s + 1) * CPU_SLICE, THRESHOLD))
+        units.append((G, im, ch, expected, MODEL, s * cpu_slice, (s + 1) * cpu_slice, THRESHOLD))
     return units
 
 
-def cpu_reference_rate(items, expected, workers, n_units=None):
+def cpu_reference_rate(items, expected, workers, n_units=None, cpu_slice=CPU_SLICE):
     """pixels/s of the oracle port over `workers` loky processes (the reference fans out the same
     way, scripts/neoloop-caller:159)."""
     from joblib import Parallel, delayed
-    units = cpu_work_units(items, expected, n_units or workers)
+    units = cpu_work_units(items, expected, n_units or workers, cpu_slice)
     t0 = time.perf_counter()
     if workers == 1:
         scored = [_cpu_score_one(u) for u in units]
@@ -222,14 +231,17 @@ def run_reference_arm(args, rank, world):
     if args.warmup > 0:
         from joblib import Parallel, delayed
         Parallel(n_jobs=workers)(delayed(int)(k) for k in range(workers))       # start the loky workers
+    # bounded sample: a step is one work unit per worker; the slice shrinks with --steps so that the whole
+    # run stays near three minutes whatever K the caller asks for (about 0.26 ms of one core per candidate)
+    cpu_slice = int(min(CPU_SLICE, max(6000, CPU_SLICE * 14 // max(1, args.steps))))
     pix, secs = 0, 0.0
     for _ in range(args.steps):
-        r, p, dt = cpu_reference_rate(items, expected, workers)
+        r, p, dt = cpu_reference_rate(items, expected, workers, cpu_slice=cpu_slice)
         pix += p
         secs += dt
     value = pix / secs
     sample = ("%d work units per step = %d assemblies x candidate slices of %d, oracle/pyport.py, joblib loky n_jobs=%d"
-              % (workers, len(items), CPU_SLICE, workers))
+              % (workers, len(items), cpu_slice, workers))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True,
