@@ -710,6 +710,86 @@ NLFO_API int nlfo_pool_bucket(const int *pi, const int *pj, const double *val, i
     return kept;
 }
 
+/* ------------------------------------------------------------------------------------
+ * Row f-2: the reference's reads of a cooler, restated on cooler's own pixel table
+ * (bin1_offset index, bin2 ascending inside a row, bin1 <= bin2, int32 counts, one weight per bin).
+ * `clr.matrix(balance=col).fetch(r1, r2)` returns the symmetric completion of the stored upper
+ * triangle, balanced as (count * w[row bin]) * w[column bin]; absent pixels are 0.
+ * ---------------------------------------------------------------------------------- */
+static double px_lookup(const int64_t *off, const int32_t *bin2, const int32_t *cnt, int64_t a, int64_t b)
+{
+    if (a > b) { int64_t t = a; a = b; b = t; }
+    int64_t lo = off[a], hi = off[a + 1];
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if (bin2[m] < b) lo = m + 1; else hi = m;
+    }
+    return (lo < off[a + 1] && bin2[lo] == b) ? (double)cnt[lo] : 0.0;
+}
+
+/* complexSV.reorganize_matrix (neoloop/assembly.py:408-492): blocks laid side by side, block k =
+ * global bins [src_lo[k], src_hi[k]) read backwards when rev[k]; every block pair j1 <= j2 is
+ * fetched, flipped per orientation and pasted (get_matrix clears NaN when balancing,
+ * assembly.py:399-406), then np.triu; bias = weights with NaN -> 0 (get_bias, assembly.py:387-397). */
+NLFO_API void nlfo_assemble_pixels(const int64_t *off, const int32_t *bin2, const int32_t *cnt, const double *w,
+                                   int balance, int nblk, const int64_t *src_lo, const int64_t *src_hi,
+                                   const unsigned char *rev, double *M, double *bias)
+{
+    long n = 0;
+    long *start = (long *)malloc(sizeof(long) * (nblk + 1));
+    for (int k = 0; k < nblk; k++) { start[k] = n; n += (long)(src_hi[k] - src_lo[k]); }
+    start[nblk] = n;
+    memset(M, 0, sizeof(double) * (size_t)n * n);
+    for (int j1 = 0; j1 < nblk; j1++) {
+        const long n1 = (long)(src_hi[j1] - src_lo[j1]);
+        for (long i = 0; i < n1; i++) {
+            const int64_t a = rev[j1] ? src_hi[j1] - 1 - i : src_lo[j1] + i;
+            double v = w[a];
+            bias[start[j1] + i] = (v != v) ? 0.0 : v;
+        }
+        for (int j2 = j1; j2 < nblk; j2++) {
+            const long n2 = (long)(src_hi[j2] - src_lo[j2]);
+            for (long i = 0; i < n1; i++) {
+                const int64_t a = rev[j1] ? src_hi[j1] - 1 - i : src_lo[j1] + i;
+                for (long j = 0; j < n2; j++) {
+                    const int64_t b = rev[j2] ? src_hi[j2] - 1 - j : src_lo[j2] + j;
+                    double v = px_lookup(off, bin2, cnt, a, b);
+                    if (balance) {
+                        v = (v * w[a]) * w[b];
+                        if (v != v) v = 0.0;
+                    }
+                    const long r = start[j1] + i, c = start[j2] + j;
+                    M[(size_t)r * n + c] = (r <= c) ? v : 0.0;          /* np.triu */
+                }
+            }
+        }
+    }
+    free(start);
+}
+
+/* util._prepare_core (neoloop/util.py:403-428) for the chromosome of global bins [lo, hi):
+ * sums[i] / cnts[i] = hic.diagonal(i)[valid].sum() / .size for i < nd, valid = both weights finite
+ * and positive; numpy's pairwise order. */
+NLFO_API void nlfo_expected_chrom(const int64_t *off, const int32_t *bin2, const int32_t *cnt, const double *w,
+                                  int balance, int64_t lo, int64_t hi, int nd, double *sums, long *cnts)
+{
+    const long n = (long)(hi - lo);
+    double *buf = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < nd; i++) {
+        long m = 0;
+        for (long r = 0; r + i < n; r++) {
+            const double wa = w[lo + r], wb = w[lo + r + i];
+            if (!(isfinite(wa) && wa > 0 && isfinite(wb) && wb > 0)) continue;
+            double v = px_lookup(off, bin2, cnt, lo + r, lo + r + i);
+            if (balance) v = (v * wa) * wb;
+            buf[m++] = v;
+        }
+        sums[i] = m ? nlfo_pairwise_sum(buf, m, 1) : 0.0;
+        cnts[i] = m;
+    }
+    free(buf);
+}
+
 NLFO_API int nlfo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -47,6 +47,11 @@ def lib():
         L.nlfo_anchor_priorities.restype = C.c_int
         L.nlfo_anchor_priorities.argtypes = [ip, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.nlfo_num_threads.restype = C.c_int
+        i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        L.nlfo_assemble_pixels.restype = None
+        L.nlfo_assemble_pixels.argtypes = [i64p, i32p, i32p, dp, C.c_int, C.c_int, i64p, i64p, bp, dp, dp]
+        L.nlfo_expected_chrom.restype = None
+        L.nlfo_expected_chrom.argtypes = [i64p, i32p, i32p, dp, C.c_int, C.c_int64, C.c_int64, C.c_int, dp, lp]
         _lib = L
     return _lib
 
@@ -227,3 +232,34 @@ def score_matrix(G, exp_arr, model_arrays, w, upper=400, lower=4):
     if len(fea32) < 2:
         return clist, np.zeros(0), fea32
     return clist, forest_predict(model_arrays, fea32), fea32
+
+
+def _pixel_table(off, bin2, cnt, w):
+    return (np.ascontiguousarray(off, dtype=np.int64), np.ascontiguousarray(bin2, dtype=np.int32),
+            np.ascontiguousarray(cnt, dtype=np.int32), _f64(w))
+
+
+def assemble_pixels(off, bin2, cnt, w, src_lo, src_hi, rev, balance=True):
+    """complexSV.reorganize_matrix on cooler's pixel table -> (fusion_matrix, bias)."""
+    off, bin2, cnt, w = _pixel_table(off, bin2, cnt, w)
+    lo = np.ascontiguousarray(src_lo, dtype=np.int64)
+    hi = np.ascontiguousarray(src_hi, dtype=np.int64)
+    rv = np.ascontiguousarray(rev, dtype=np.uint8)
+    n = int((hi - lo).sum())
+    M = np.empty((n, n), dtype=np.float64)
+    bias = np.empty(n, dtype=np.float64)
+    lib().nlfo_assemble_pixels(_p(off, C.c_int64), _p(bin2, C.c_int32), _p(cnt, C.c_int32), _p(w, C.c_double),
+                               1 if balance else 0, len(lo), _p(lo, C.c_int64), _p(hi, C.c_int64), _p(rv, C.c_ubyte),
+                               _p(M, C.c_double), _p(bias, C.c_double))
+    return M, bias
+
+
+def expected_chrom(off, bin2, cnt, w, lo, hi, nd, balance=True):
+    """util._prepare_core on cooler's pixel table -> (sums[nd], counts[nd])."""
+    off, bin2, cnt, w = _pixel_table(off, bin2, cnt, w)
+    nd = min(int(nd), int(hi) - int(lo))
+    sums = np.empty(nd, dtype=np.float64)
+    cnts = np.empty(nd, dtype=np.int64)
+    lib().nlfo_expected_chrom(_p(off, C.c_int64), _p(bin2, C.c_int32), _p(cnt, C.c_int32), _p(w, C.c_double),
+                              1 if balance else 0, int(lo), int(hi), nd, _p(sums, C.c_double), _p(cnts, C.c_long))
+    return sums, cnts

@@ -46,6 +46,13 @@ def test_assembly_matrix_from_pixels(maps, ID, col):
     assert np.array_equal(fu.bias, want.bias)
     assert np.array_equal(fu.fusion_matrix, want.fusion_matrix)
     assert fu.fusion_matrix.any()
+    # and the plain-C restatement on the same pixel table
+    from oracle import coracle as co
+    spans = [px.global_bins(*px._bin_extent(tuple(r))) for r in fu.blocks]
+    M, bias = co.assemble_pixels(px.bin1_offset, px.bin2, px.count, px._w["weight" if col is False else col],
+                                 [a for a, _b in spans], [b for _a, b in spans], [o == '-' for o in fu.orients],
+                                 balance=bool(col))
+    assert np.array_equal(fu.fusion_matrix, M) and np.array_equal(fu.bias, bias)
 
 
 def test_pipeline_from_pixels_equals_port(maps):
@@ -82,6 +89,15 @@ def test_expected_from_pixels(balance):
         got = calculate_expected(px, chroms, maxdis=maxdis, balance=balance)
         assert list(got) == list(want) and len(want) == maxdis // 10000 + 1
         assert all(got[k] == want[k] for k in want), (balance, maxdis)
+    # raw per-chromosome sums and counts against the plain-C restatement (6 000-bin and 300-bin chromosomes)
+    from oracle import coracle as co
+    col = "weight" if isinstance(balance, bool) else balance
+    dp = px.device_pixels(None, col)
+    for c in ("chr1", "chr2"):
+        lo, hi = px.global_bins(c, 0, px._nbins(c))
+        sums, cnts = dp.expected_diagonals(lo, hi, 201, balance=bool(balance))
+        ws, wc = co.expected_chrom(px.bin1_offset, px.bin2, px.count, px._w[col], lo, hi, 201, balance=bool(balance))
+        assert np.array_equal(cnts, wc) and np.array_equal(sums, ws), (balance, c)
 
 
 def test_chromosomes_from_pixels_equal_host_band():

@@ -98,3 +98,41 @@ def test_real_reference_reads_the_same_from_the_pixel_table(pair):
         ea = ru._prepare_core((clr, "chr1", 250, bal))
         eb = ru._prepare_core((px, "chr1", 250, bal))
         assert ea.keys() == eb.keys() and all(ea[k][0] == eb[k][0] and ea[k][1] == eb[k][1] for k in ea)
+
+
+def _blocks_of(px, fu):
+    spans = [px.global_bins(*px._bin_extent(tuple(r))) for r in fu.blocks]
+    return [a for a, _b in spans], [b for _a, b in spans], [o == '-' for o in fu.orients]
+
+
+def test_c_oracle_restates_the_pixel_table_reads(pair):
+    """oracle/c: reorganize_matrix and _prepare_core on the pixel table equal the Python port reading the
+    same table through the cooler surface (and, in the build container, the real reference above)."""
+    from neoloopfinder_b200.assembly import complexSV
+    from oracle import coracle as co
+    from oracle import pyport
+    _clr, px = pair
+    lines = ["translocation,1,1200000,+,2,800000,-\t1,600000\t2,1400000",
+             "inversion,3,400000,+,3,900000,+\t3,0\t3,500000",
+             "inversion,3,400000,-,3,900000,-\t3,800000\t3,1300000",
+             "translocation,1,1200000,+,2,800000,-\tinversion,2,1500000,+,3,900000,+\t1,600000\t3,300000",
+             "duplication,1,1000000,-,1,1200000,+\t1,1500000\t1,700000"]
+    for line in lines:
+        for col in ("sweight", "weight", False):
+            want = pyport.AssemblyPort(px, line, span=600000, col=col, expected_values={}, flexible=False)
+            want.reorganize_matrix()
+            geo = complexSV(px, line, span=600000, col=col, expected_values={}, flexible=False)
+            geo.reorganize_matrix(map_only=True)              # geometry only: no device involved
+            assert geo.index == want.index
+            lo, hi, rev = _blocks_of(px, geo)
+            w = px._w["weight" if col is False else col]
+            M, bias = co.assemble_pixels(px.bin1_offset, px.bin2, px.count, w, lo, hi, rev, balance=bool(col))
+            assert np.array_equal(M, want.fusion_matrix), (line, col)
+            assert np.array_equal(bias, want.bias), (line, col)
+    for bal in ("sweight", True, False):
+        want = pyport.chrom_expected((px, "chr1", 250, bal))
+        lo, hi = px.global_bins("chr1", 0, px._nbins("chr1"))
+        sums, cnts = co.expected_chrom(px.bin1_offset, px.bin2, px.count, px._w["weight" if isinstance(bal, bool) else bal],
+                                       lo, hi, 251, balance=bool(bal))
+        assert set(want) == {i for i in range(251) if cnts[i] > 0}
+        assert all(want[i][0] == sums[i] and want[i][1] == cnts[i] for i in want)
