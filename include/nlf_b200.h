@@ -214,6 +214,18 @@ int nlf_pool_peak_heights(nlf_ctx *ctx, int n_buckets, const int64_t *bucket_off
                           int res, int min_count, int r_bp, double *prio_out, int64_t *prio_off,
                           int *ambiguous);
 
+/* Peakachu.find_anchors (callers.py:740-784) for one coordinate list: anchors_out[3*k ..] =
+ * (summit, left bound, right bound) of anchor k; cap >= max(pos) - min(pos) + 1.  min_dis_bp is the
+ * method's min_dis (bp); order: optional numpy.argsort permutation of the peak heights (see
+ * nlf_pool_peak_heights), NULL = stable order. */
+int nlf_pool_find_anchors(nlf_ctx *ctx, const int *pos, int npos, int res, int min_count, int min_dis_bp,
+                          const int *order, int *anchors_out, int cap, int *n_anchors);
+/* Peakachu._cluster_core (callers.py:786-831) on points already sorted by descending
+ * (value, (i, j)): is_final_out[k] = 1 when point k is appended to final_list, pooled_out[k] = 1
+ * when it joins `visited`.  r_bins is the method's r (bins). */
+int nlf_pool_cluster_core(nlf_ctx *ctx, const int *pi, const int *pj, int m, int r_bins,
+                          uint8_t *is_final_out, uint8_t *pooled_out);
+
 #ifdef __cplusplus
 }
 #endif

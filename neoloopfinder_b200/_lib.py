@@ -82,6 +82,8 @@ _SIGNATURES = {
     "nlf_batch_njobs": (C.c_int, [vp]),
     "nlf_batch_destroy": (C.c_int, [vp]),
     "nlf_pool": (C.c_int, [vp, C.c_int, i64p, ip, ip, dp, C.c_int, C.c_int, C.c_int, ip, i64p, ip, i64p, u8p]),
+    "nlf_pool_find_anchors": (C.c_int, [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, ip]),
+    "nlf_pool_cluster_core": (C.c_int, [vp, ip, ip, C.c_int, C.c_int, u8p, u8p]),
     "nlf_pool_peak_heights": (C.c_int, [vp, C.c_int, i64p, ip, C.c_int, C.c_int, C.c_int, dp, i64p, ip]),
 }
 

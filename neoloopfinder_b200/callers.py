@@ -586,6 +586,56 @@ class Peakachu():
         mask = pool_buckets([(ij[:, 0], ij[:, 1], val)], self.r, min_count, r, self._ctx)[0]
         return [(int(a), int(b)) for a, b in ij[mask]]
 
+    def find_anchors(self, pos, min_count=3, min_dis=15000, wlen=40000):
+        """Anchors {(summit, left, right)} of one coordinate list (callers.py:740-784): histogram peaks at least
+        ``min_count`` high and ``min_dis`` apart, widened to the foot of each peak, merged on overlap.  Runs on the
+        GPU (the routine the pooling kernel uses); below 10 kb ties between equal peak heights follow
+        numpy.argsort, exactly like the pooling path."""
+        import ctypes as C
+        if wlen != 40000:
+            raise NotImplementedError("find_anchors: only the reference's window length (40000 bp) is built in")
+        pos = np.ascontiguousarray(list(pos), dtype=np.int32)
+        if pos.size == 0:
+            raise ValueError("min() arg is an empty sequence")              # Counter of nothing, as in the reference
+        L = _lib.load()
+        order = None
+        if max(min_dis // self.r, 2) > 2:
+            off = np.array([0, pos.size], dtype=np.int64)
+            prio = np.empty(pos.size, dtype=np.float64)
+            poff = np.zeros(2, dtype=np.int64)
+            amb = C.c_int(0)
+            _lib.check(L.nlf_pool_peak_heights(self._ctx.h, 1, _lib.ptr(off, C.c_int64), _lib.ptr(pos, C.c_int), int(self.r),
+                                               int(min_count), int(min_dis), _lib.ptr(prio, C.c_double),
+                                               _lib.ptr(poff, C.c_int64), C.byref(amb)))
+            if amb.value:
+                order = np.zeros(pos.size, dtype=np.int32)
+                order[:int(poff[1])] = np.argsort(prio[:int(poff[1])])        # default kind, as scipy calls it
+        cap = int(pos.max() - pos.min()) + 1
+        out = np.empty(3 * cap, dtype=np.int32)
+        n = C.c_int(0)
+        _lib.check(L.nlf_pool_find_anchors(self._ctx.h, _lib.ptr(pos, C.c_int), int(pos.size), int(self.r), int(min_count),
+                                           int(min_dis), None if order is None else _lib.ptr(order, C.c_int),
+                                           _lib.ptr(out, C.c_int), cap, C.byref(n)))
+        return {(int(a), int(b), int(c)) for a, b, c in out[:3 * n.value].reshape(-1, 3)}
+
+    def _cluster_core(self, sort_list, r, visited, final_list):
+        """DBSCAN + greedy pooling of one sorted point list (callers.py:786-831): seeds are appended to
+        ``final_list``, every pooled point joins ``visited``.  ``r`` is in bins."""
+        import ctypes as C
+        pts = [p[1] for p in sort_list]
+        m = len(pts)
+        if m == 0:
+            return
+        ij = np.ascontiguousarray(pts, dtype=np.int32).reshape(m, 2)
+        pi, pj = np.ascontiguousarray(ij[:, 0]), np.ascontiguousarray(ij[:, 1])
+        fin = np.zeros(m, dtype=np.uint8)
+        pooled = np.zeros(m, dtype=np.uint8)
+        _lib.check(_lib.load().nlf_pool_cluster_core(self._ctx.h, _lib.ptr(pi, C.c_int), _lib.ptr(pj, C.c_int), m, int(r),
+                                                     _lib.ptr(fin, C.c_ubyte), _lib.ptr(pooled, C.c_ubyte)))
+        for k in np.flatnonzero(fin):
+            final_list.append((int(pi[k]), int(pj[k])))
+        visited.update((int(pi[k]), int(pj[k])) for k in np.flatnonzero(pooled))
+
     def close(self):
         self._batch.close()
 

@@ -711,3 +711,97 @@ NLF_EXPORT int nlf_pool_peak_heights(nlf_ctx *ctx, int n_buckets, const int64_t 
     cudaFreeAsync(d_pos, s); cudaFreeAsync(d_prio, s); cudaFreeAsync(d_np, s); cudaFreeAsync(d_amb, s);
     return NLF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The two helper methods of Peakachu as callable entry points (the pooling kernel uses the same
+// device routines): find_anchors (callers.py:740-784) and _cluster_core (callers.py:786-831).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_find_anchors_one(const int *pos, int npos, int res, int min_count, int r_bp, const int *order,
+                                   char *ws_base, int range, int *out, int *n_out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    BucketWs ws = carve(ws_base, range, npos);
+    const int k = d_find_anchors(pos, npos, res, min_count, r_bp, ws, ws.xa, order, 0, nullptr, nullptr, nullptr);
+    for (int q = 0; q < k; q++) { out[3 * q] = ws.xa[q].summit; out[3 * q + 1] = ws.xa[q].lb; out[3 * q + 2] = ws.xa[q].rb; }
+    *n_out = k;
+}
+
+__global__ void __launch_bounds__(256) k_cluster_core_one(const int *pi, const int *pj, int m, int r, char *ws_base,
+                                                          unsigned char *is_final, unsigned char *pooled)
+{
+    BucketWs ws = carve(ws_base, 1, m);
+    for (int a = threadIdx.x; a < m; a += blockDim.x) { ws.visited[a] = 0; ws.is_final[a] = 0; ws.sl[a] = a; }
+    __syncthreads();
+    d_cluster_core(ws.sl, m, r, pi, pj, ws);
+    __syncthreads();
+    for (int a = threadIdx.x; a < m; a += blockDim.x) { is_final[a] = ws.is_final[a]; pooled[a] = ws.visited[a]; }
+}
+
+NLF_EXPORT int nlf_pool_find_anchors(nlf_ctx *ctx, const int *pos, int npos, int res, int min_count, int min_dis_bp,
+                                     const int *order, int *anchors_out, int cap, int *n_anchors)
+{
+    if (!ctx || !pos || npos <= 0 || res <= 0 || !anchors_out || !n_anchors) return fail(NLF_ERR_ARG, "nlf_pool_find_anchors: bad arguments");
+    int lo = pos[0], hi = pos[0];
+    for (int i = 1; i < npos; i++) { lo = std::min(lo, pos[i]); hi = std::max(hi, pos[i]); }
+    const int range = std::max(hi - lo + 1, npos) + 2;
+    if (cap < hi - lo + 1) return fail(NLF_ERR_ARG, "nlf_pool_find_anchors: anchors_out needs room for %d anchors", hi - lo + 1);
+    nlf_ctx *c = ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int *d_pos, *d_out, *d_n, *d_order = nullptr;
+    char *d_ws;
+    NLF_CUDA(cudaMallocAsync(&d_pos, sizeof(int) * npos, s));
+    NLF_CUDA(cudaMallocAsync(&d_out, sizeof(int) * 3 * (size_t)range, s));
+    NLF_CUDA(cudaMallocAsync(&d_n, sizeof(int), s));
+    NLF_CUDA(cudaMallocAsync(&d_ws, pool_ws_bytes(range, npos + 1) + 256, s));
+    NLF_CUDA(cudaMemcpyAsync(d_pos, pos, sizeof(int) * npos, cudaMemcpyHostToDevice, s));
+    if (order) {
+        NLF_CUDA(cudaMallocAsync(&d_order, sizeof(int) * range, s));
+        NLF_CUDA(cudaMemcpyAsync(d_order, order, sizeof(int) * std::min(range, npos), cudaMemcpyHostToDevice, s));
+    }
+    {
+        KLaunch k(c, P_POOL);
+        k_find_anchors_one<<<1, 32, 0, s>>>(d_pos, npos, res, min_count, min_dis_bp, d_order, d_ws, range, d_out, d_n);
+    }
+    NLF_CUDA(cudaGetLastError());
+    int n = 0;
+    NLF_CUDA(cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    if (n > 0) NLF_CUDA(cudaMemcpyAsync(anchors_out, d_out, sizeof(int) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    *n_anchors = n;
+    cudaFreeAsync(d_pos, s); cudaFreeAsync(d_out, s); cudaFreeAsync(d_n, s); cudaFreeAsync(d_ws, s);
+    if (d_order) cudaFreeAsync(d_order, s);
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_pool_cluster_core(nlf_ctx *ctx, const int *pi, const int *pj, int m, int r_bins,
+                                     uint8_t *is_final_out, uint8_t *pooled_out)
+{
+    if (!ctx || m < 0 || (m > 0 && (!pi || !pj || !is_final_out || !pooled_out)) || r_bins < 0)
+        return fail(NLF_ERR_ARG, "nlf_pool_cluster_core: bad arguments");
+    if (m == 0) return NLF_OK;
+    nlf_ctx *c = ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int *d_pi, *d_pj;
+    unsigned char *d_fin, *d_pool;
+    char *d_ws;
+    NLF_CUDA(cudaMallocAsync(&d_pi, sizeof(int) * m, s));
+    NLF_CUDA(cudaMallocAsync(&d_pj, sizeof(int) * m, s));
+    NLF_CUDA(cudaMallocAsync(&d_fin, m, s));
+    NLF_CUDA(cudaMallocAsync(&d_pool, m, s));
+    NLF_CUDA(cudaMallocAsync(&d_ws, pool_ws_bytes(1, m + 1) + 256, s));
+    NLF_CUDA(cudaMemcpyAsync(d_pi, pi, sizeof(int) * m, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_pj, pj, sizeof(int) * m, cudaMemcpyHostToDevice, s));
+    {
+        KLaunch k(c, P_POOL);
+        k_cluster_core_one<<<1, 256, 0, s>>>(d_pi, d_pj, m, r_bins, d_ws, d_fin, d_pool);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaMemcpyAsync(is_final_out, d_fin, m, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaMemcpyAsync(pooled_out, d_pool, m, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    cudaFreeAsync(d_pi, s); cudaFreeAsync(d_pj, s); cudaFreeAsync(d_fin, s); cudaFreeAsync(d_pool, s); cudaFreeAsync(d_ws, s);
+    return NLF_OK;
+}

@@ -362,3 +362,39 @@ def test_gap_columns_with_negative_and_cancelling_entries(gpu):
     assert np.array_equal(asm.kept_index(), want)
     assert not {10, 20, 30, 70} & set(want.tolist()) and {40, 50, 60} <= set(want.tolist())
     asm.close()
+
+
+@pytest.mark.parametrize("res", [5000, 10000, 25000])
+def test_find_anchors_and_cluster_core_methods(res, gpu):
+    """Peakachu.find_anchors / _cluster_core as callable methods against the port, which
+    makes the reference's scipy / sklearn calls."""
+    from neoloopfinder_b200.callers import Peakachu
+    from oracle import pyport
+    rng = np.random.default_rng(res)
+    n = 120
+    G = np.triu(rng.random((n, n)))
+    mine = Peakachu(G, upper=100 * res, res=res)
+    port = pyport.PeakachuPort(G, upper=100 * res, res=res)
+    for trial in range(25):
+        centres = rng.integers(20, 400, size=int(rng.integers(1, 8)))
+        pos = np.concatenate([rng.integers(c - 6, c + 7, size=int(rng.integers(2, 30))) for c in centres])
+        pos = np.concatenate([pos, rng.integers(0, 420, size=int(rng.integers(0, 12)))]).tolist()
+        for mc in (2, 3):
+            try:
+                want = port.find_anchors(pos, min_count=mc, min_dis=15000)
+            except Exception as exc:                                  # noqa: BLE001 - scipy refuses degenerate inputs
+                pytest.skip("port raised %r" % (exc,))
+            assert mine.find_anchors(pos, min_count=mc, min_dis=15000) == want, (trial, mc)
+    for trial in range(25):
+        m = int(rng.integers(1, 60))
+        pts = set()
+        while len(pts) < m:
+            c = rng.integers(10, 100, size=2)
+            pts.add((int(c[0] + rng.integers(-4, 5)), int(c[1] + rng.integers(-4, 5))))
+        sort_list = sorted(((float(rng.integers(1, 9)), p) for p in pts), reverse=True)
+        r = max(15000 // res, 2)
+        v1, f1, v2, f2 = set(), [], set(), []
+        port._cluster_core(list(sort_list), r, v2, f2)
+        mine._cluster_core(list(sort_list), r, v1, f1)
+        assert f1 == f2 and v1 == {(int(a), int(b)) for a, b in v2}, trial
+    mine.close()
