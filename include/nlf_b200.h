@@ -191,6 +191,12 @@ int nlf_batch_fetch_features32(nlf_batch *b, int job, long long cap, float *fea)
 int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const int *yi, long long nc, int w,
                         const double *expected, int nexp, const double *gw, int radius,
                         double *fea, int *clist, long long *n_rows);
+/* util.distance_normalize + distance_normaize_core (neoloop/util.py:470-524) on a caller-provided stack of
+ * N windows ((2w+1)^2 doubles each, centred at (xi, yi)): NaN -> 0, the count_nonzero and lower-left-mean
+ * gates, observed / expected.  out receives every window (normalised when it passes and its largest
+ * distance is inside the expected table), pass[k] = 1 when window k is kept. */
+int nlf_distance_normalize(nlf_ctx *ctx, const double *windows, long long N, const int *xi, const int *yi,
+                           int w, const double *expected, int nexp, double *out, uint8_t *pass);
 /* Drop the results but keep the matrices resident, so nlf_batch_score can run again. */
 int nlf_batch_reset(nlf_batch *b);
 int nlf_batch_njobs(nlf_batch *b);

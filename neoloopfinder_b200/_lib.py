@@ -78,6 +78,7 @@ _SIGNATURES = {
     "nlf_batch_fetch_candidates": (C.c_int, [vp, C.c_int, C.c_longlong, ip, ip]),
     "nlf_batch_fetch_features32": (C.c_int, [vp, C.c_int, C.c_longlong, fp]),
     "nlf_batch_getwindow": (C.c_int, [vp, C.c_int, ip, ip, C.c_longlong, C.c_int, dp, C.c_int, dp, C.c_int, dp, ip, llp]),
+    "nlf_distance_normalize": (C.c_int, [vp, dp, C.c_longlong, ip, ip, C.c_int, dp, C.c_int, dp, u8p]),
     "nlf_batch_reset": (C.c_int, [vp]),
     "nlf_batch_njobs": (C.c_int, [vp]),
     "nlf_batch_destroy": (C.c_int, [vp]),

@@ -2236,6 +2236,95 @@ NLF_EXPORT int nlf_batch_keep_features(nlf_batch *b, int on)
     return NLF_OK;
 }
 
+// util.distance_normalize (neoloop/util.py:499-524) + distance_normaize_core (:470-491) on a stack of
+// windows handed over by the caller: NaN -> 0, count_nonzero and lower-left-mean gates, O/E division.
+// One warp per window; the w x w mean is numpy's (8-accumulator) order, computed by one lane.
+__global__ void __launch_bounds__(128) k_distance_normalize(const double *__restrict__ win, long long N, const int *__restrict__ xi,
+                                                            const int *__restrict__ yi, int w, const double *__restrict__ expv,
+                                                            int nexp, double *__restrict__ out, unsigned char *__restrict__ pass)
+{
+    __shared__ double tmp[4][15 * 15];
+    __shared__ double s_ll[4];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const long long k = (long long)blockIdx.x * 4 + wp;
+    if (k >= N) return;
+    const int S = 2 * w + 1, F = S * S;
+    const double *src = win + (size_t)k * F;
+    double *dst = out + (size_t)k * F;
+    int nz = 0;
+    for (int c = lane; c < F; c += 32) {
+        double v = src[c];
+        if (v != v) v = 0.0;
+        tmp[wp][c] = v;
+        nz += (v != 0.0);
+    }
+    for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    __syncwarp();
+    bool ok = !((double)nz < __dmul_rn((double)F, 0.1));
+    if (ok) {
+        if (lane == 0) {
+            const double *t = tmp[wp];
+            auto ld = [&](int q) { return t[(q / w) * S + (q % w)]; };
+            s_ll[wp] = __ddiv_rn((w * w <= 128) ? np_leaf_sum(ld, 0, w * w) : np_pairwise_sum(ld, w * w), (double)(w * w));
+        }
+        __syncwarp();
+        const double ll = s_ll[wp];
+        ok = (ll > 0) && (__ddiv_rn(tmp[wp][w * S + w], ll) > 0.1);
+    }
+    if (ok) {
+        const int x = xi[k], y = yi[k];
+        int dmax = abs(y - x) + 2 * w;                          // largest |column - row| inside the window
+        const bool normalise = dmax < nexp;
+        for (int c = lane; c < F; c += 32) {
+            const int a = c / S, b = c % S;
+            const int d = abs((y - w + b) - (x - w + a));
+            const double v = tmp[wp][c];
+            dst[c] = normalise ? __ddiv_rn(v, expv[d]) : v;
+        }
+    } else {
+        for (int c = lane; c < F; c += 32) dst[c] = tmp[wp][c];
+    }
+    if (lane == 0) pass[k] = ok ? 1 : 0;
+}
+
+NLF_EXPORT int nlf_distance_normalize(nlf_ctx *ctx, const double *windows, long long N, const int *xi, const int *yi,
+                                      int w, const double *expected, int nexp, double *out, uint8_t *pass)
+{
+    if (!ctx || N < 0 || w < 1 || w > 7 || nexp <= 0 || !expected || (N > 0 && (!windows || !xi || !yi || !out || !pass)))
+        return fail(NLF_ERR_ARG, "nlf_distance_normalize: bad arguments (w must be 1..7)");
+    if (N == 0) return NLF_OK;
+    nlf_ctx *c = ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t F = (size_t)(2 * w + 1) * (2 * w + 1);
+    double *d_win, *d_out, *d_exp;
+    int *d_xy;
+    unsigned char *d_pass;
+    NLF_CUDA(c->big_alloc((void **)&d_win, sizeof(double) * F * N));
+    NLF_CUDA(c->big_alloc((void **)&d_out, sizeof(double) * F * N));
+    NLF_CUDA(cudaMallocAsync(&d_exp, sizeof(double) * nexp, s));
+    NLF_CUDA(cudaMallocAsync(&d_xy, sizeof(int) * 2 * N, s));
+    NLF_CUDA(cudaMallocAsync(&d_pass, N, s));
+    NLF_CUDA(cudaMemcpyAsync(d_win, windows, sizeof(double) * F * N, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_exp, expected, sizeof(double) * nexp, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_xy, xi, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+    NLF_CUDA(cudaMemcpyAsync(d_xy + N, yi, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+    {
+        KLaunch k(c, P_FEATURE);
+        k_distance_normalize<<<(unsigned)((N + 3) / 4), 128, 0, s>>>(d_win, N, d_xy, d_xy + N, w, d_exp, nexp, d_out, d_pass);
+    }
+    NLF_CUDA(cudaGetLastError());
+    NLF_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * F * N, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaMemcpyAsync(pass, d_pass, N, cudaMemcpyDeviceToHost, s));
+    NLF_CUDA(cudaStreamSynchronize(s));
+    c->big_free(d_win);
+    c->big_free(d_out);
+    NLF_CUDA(cudaFreeAsync(d_exp, s));
+    NLF_CUDA(cudaFreeAsync(d_xy, s));
+    NLF_CUDA(cudaFreeAsync(d_pass, s));
+    return NLF_OK;
+}
+
 NLF_EXPORT int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const int *yi, long long nc, int w,
                                    const double *expected, int nexp, const double *gw, int radius, double *fea,
                                    int *clist, long long *n_rows)

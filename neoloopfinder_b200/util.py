@@ -160,8 +160,29 @@ def image_normalize(arr_2d):
     return (arr_2d - arr_2d.min()) / (arr_2d.max() - arr_2d.min())
 
 
-def distance_normalize(*_args, **_kwargs):
-    raise NotImplementedError(
-        "distance_normalize operates on host window stacks in the reference (neoloop/util.py:499-524); "
-        "in neoloopfinder_b200 the gates and the O/E transform are fused into the CUDA feature kernel: "
-        "call Peakachu.getwindow(coords, w) instead")
+def distance_normalize(arr_pool, exp_bychrom, xi, yi, w):
+    """Gates and observed/expected transform of a stack of windows (neoloop/util.py:499-524): NaN -> 0 (in place,
+    as the reference does), windows with fewer than 10 % non-zero cells, a non-positive lower-left mean or a
+    centre below 0.1 of it are dropped, the others are divided by the expected at each cell's distance unless the
+    window reaches beyond the expected table.  Returns (list of windows, list of (x, y)).  On the scoring path this
+    is fused into the feature kernel; this entry serves callers that hold their own window stacks."""
+    import ctypes as C
+    from . import _lib
+    xi = np.ascontiguousarray(xi, dtype=np.int32)
+    yi = np.ascontiguousarray(yi, dtype=np.int32)
+    n = int(xi.size)
+    S = 2 * int(w) + 1
+    if n == 0:
+        return [], []
+    if isinstance(arr_pool, np.ndarray) and arr_pool.dtype == np.float64:
+        arr_pool[np.isnan(arr_pool)] = 0                      # the reference clears NaN inside the caller's stack
+    stack = np.ascontiguousarray(np.asarray(arr_pool, dtype=np.float64)[:n]).reshape(n, S, S)
+    exp = np.ascontiguousarray(exp_bychrom, dtype=np.float64)
+    out = np.empty_like(stack)
+    keep = np.zeros(n, dtype=np.uint8)
+    ctx = _lib.Context.get()
+    _lib.check(_lib.load().nlf_distance_normalize(ctx.h, _lib.ptr(stack, C.c_double), n, _lib.ptr(xi, C.c_int),
+                                                  _lib.ptr(yi, C.c_int), int(w), _lib.ptr(exp, C.c_double), int(exp.size),
+                                                  _lib.ptr(out, C.c_double), _lib.ptr(keep, C.c_ubyte)))
+    sel = np.flatnonzero(keep)
+    return [out[k] for k in sel], [(xi[k], yi[k]) for k in sel]

@@ -398,3 +398,30 @@ def test_find_anchors_and_cluster_core_methods(res, gpu):
         mine._cluster_core(list(sort_list), r, v1, f1)
         assert f1 == f2 and v1 == {(int(a), int(b)) for a, b in v2}, trial
     mine.close()
+
+
+@pytest.mark.parametrize("w,nexp", [(6, 501), (5, 60), (7, 1001)])
+def test_distance_normalize_on_window_stacks(w, nexp, gpu):
+    """util.distance_normalize as a standalone call against the port: NaN cells, sparse windows,
+    zero lower-left corners, weak centres and windows that reach beyond the expected table."""
+    from neoloopfinder_b200.util import distance_normalize
+    from oracle import pyport
+    rng = np.random.default_rng(100 + w)
+    S, n = 2 * w + 1, 400
+    pool = rng.poisson(2.0, size=(n, S, S)).astype(float) * rng.uniform(0.01, 0.2, size=(n, S, S))
+    pool[rng.random((n, S, S)) < 0.05] = np.nan
+    pool[:60][rng.random((60, S, S)) < 0.93] = 0.0             # fail the 10 % non-zero gate
+    pool[60:100, :w, :w] = 0.0                                 # lower-left mean 0
+    pool[100:140, w, w] *= 1e-3                                # centre below 0.1 of the corner mean
+    xi = rng.integers(w, 300, size=n).astype(np.int64)
+    yi = xi + rng.integers(w + 2, 90, size=n)
+    exp = 1.0 / (np.arange(nexp) + 1.0)
+    a, b = pool.copy(), pool.copy()
+    want_fea, want_cl = pyport.distance_normalize(a, exp, xi, yi, w)
+    got_fea, got_cl = distance_normalize(b, exp, xi, yi, w)
+    assert [tuple(map(int, c)) for c in got_cl] == [tuple(map(int, c)) for c in want_cl]
+    assert 100 < len(want_cl) < n - 100
+    assert all(np.array_equal(x, y) for x, y in zip(got_fea, want_fea))
+    assert np.array_equal(a, b, equal_nan=True) and not np.isnan(b).any()      # NaN cleared in the caller's stack
+    if nexp == 60:
+        assert any((y - x) + 2 * w >= nexp for x, y in want_cl)               # some windows stay un-normalised
