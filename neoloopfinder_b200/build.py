@@ -29,6 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd += ["-ldl"]                                   # nvtx3 (header-only) loads the tool injection library lazily
     subprocess.check_call(cmd)
     return OUT
 

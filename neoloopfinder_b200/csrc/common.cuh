@@ -1,6 +1,7 @@
 // common.cuh -- shared host/device plumbing of libnlf_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a tool (ncu --nvtx, nsys) is attached
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -279,8 +280,18 @@ int nlf_pixels_export_band(nlf_pixels *px, int balance, long long lo, long long 
 // RAII-free helper: launch bracket used as  { KLaunch k(ctx, cls); kernel<<<...>>>(...); }
 struct KLaunch {
     nlf_ctx *c; int cls; cudaEvent_t a = nullptr; cudaStream_t s;
-    KLaunch(nlf_ctx *ctx, int cls_, cudaStream_t st = nullptr) : c(ctx), cls(cls_), s(st ? st : ctx->stream) { c->prof_begin(cls, &a, s); }
-    ~KLaunch() { c->prof_end(cls, a, s); }
+    static const char *range_name(int cls)
+    {
+        static const char *const names[nlf::P_NCLASS] = {"nlf:bandify", "nlf:diag_means+isotonic", "nlf:features", "nlf:forest",
+                                                         "nlf:threshold", "nlf:normalise", "nlf:pool", "nlf:other"};
+        return names[(cls >= 0 && cls < nlf::P_NCLASS) ? cls : nlf::P_NCLASS - 1];
+    }
+    KLaunch(nlf_ctx *ctx, int cls_, cudaStream_t st = nullptr) : c(ctx), cls(cls_), s(st ? st : ctx->stream)
+    {
+        nvtxRangePushA(range_name(cls));          // NVTX range around every launch: `ncu --nvtx --nvtx-include "nlf:features/"`
+        c->prof_begin(cls, &a, s);
+    }
+    ~KLaunch() { c->prof_end(cls, a, s); nvtxRangePop(); }
 };
 
 // ---------------------------------------------------------------------------------------------
