@@ -637,8 +637,21 @@ class PixelCooler(_CoolerBase):
             off += nb[c]
         rows_b2, rows_cnt, indptr = [], [], [0]
         nnz = 0
+        # sources that can emit a chromosome's band directly (no dense blocks): one vectorised pass per chromosome
+        band_source = band_bins is not None and not trans and hasattr(clr, "fetch_band")
         for i1, c1 in enumerate(names):
             n1 = nb[c1]
+            if band_source:
+                B = np.asarray(clr.fetch_band(c1, band_bins + 1, balance=False))
+                if not np.array_equal(B, np.round(B)):
+                    raise ValueError("PixelCooler stores integer counts (cooler's int32 `count` column)")
+                rr, dd = np.nonzero(B)                        # row-major: rows ascending, distances ascending inside a row
+                rows_b2.append((rr + dd + offs[c1]).astype(np.int32))
+                rows_cnt.append(B[rr, dd].astype(np.int32))
+                per_row = np.bincount(rr, minlength=n1)
+                indptr.extend((nnz + np.cumsum(per_row)).tolist())
+                nnz += int(per_row.sum())
+                continue
             for lo in range(0, n1, row_chunk):
                 hi = min(n1, lo + row_chunk)
                 per_row_b2 = [[] for _ in range(hi - lo)]
