@@ -136,3 +136,51 @@ def test_c_oracle_restates_the_pixel_table_reads(pair):
                                        lo, hi, 251, balance=bool(bal))
         assert set(want) == {i for i in range(251) if cnts[i] > 0}
         assert all(want[i][0] == sums[i] and want[i][1] == cnts[i] for i in want)
+
+
+def test_c_oracle_pixel_reads_against_dense_numpy():
+    """Randomised: small symmetric count matrices with NaN weights; blocks in any order, reversed, overlapping,
+    empty; raw and balanced.  The dense construction below is the reference's own recipe (fetch every block
+    pair, flip per orientation, paste, np.triu, NaN -> 0; per-diagonal masked sums)."""
+    from oracle import coracle as co
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        n = int(rng.integers(6, 40))
+        Cm = np.triu(rng.poisson(1.2, size=(n, n)))
+        Cm = Cm + np.triu(Cm, 1).T                                   # symmetric counts
+        w = rng.uniform(0.05, 0.2, n)
+        w[rng.random(n) < 0.15] = np.nan
+        up = np.triu(Cm)
+        rows, cols = np.nonzero(up)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=n), out=off[1:])
+        bin2, cnt = cols.astype(np.int32), up[rows, cols].astype(np.int32)
+        nblk = int(rng.integers(1, 5))
+        lo = rng.integers(0, n, size=nblk)
+        hi = np.minimum(n, lo + rng.integers(0, 12, size=nblk))
+        rev = rng.random(nblk) < 0.5
+        for balance in (True, False):
+            S = Cm.astype(float)
+            if balance:
+                S = S * w[:, None] * w[None, :]
+            idx = [np.arange(a, b)[::-1] if r else np.arange(a, b) for a, b, r in zip(lo, hi, rev)]
+            order = np.concatenate(idx) if idx else np.zeros(0, int)
+            M = S[np.ix_(order, order)]
+            # only block pairs j1 <= j2 are pasted, then np.triu
+            start = np.r_[0, np.cumsum([len(i) for i in idx])]
+            for j1 in range(nblk):
+                for j2 in range(j1):
+                    M[start[j1]:start[j1 + 1], start[j2]:start[j2 + 1]] = 0
+            M = np.triu(M)
+            if balance:
+                M[np.isnan(M)] = 0
+            bias = np.where(np.isnan(w[order]), 0.0, w[order])
+            gotM, gotb = co.assemble_pixels(off, bin2, cnt, w, lo, hi, rev, balance=balance)
+            assert np.array_equal(gotM, M) and np.array_equal(gotb, bias), (trial, balance)
+            # per-diagonal masked sums over the whole "chromosome"
+            sums, cnts = co.expected_chrom(off, bin2, cnt, w, 0, n, n, balance=balance)
+            valid = np.isfinite(w) & (w > 0)
+            for i in range(n):
+                v = valid[:n - i] & valid[i:]
+                cur = np.diagonal(S, i)[v]
+                assert cnts[i] == cur.size and (cur.size == 0 or sums[i] == cur.sum()), (trial, balance, i)
