@@ -174,3 +174,34 @@ def test_pixel_table_is_validated():
         DevicePixels(off, [0, 3, 1], [5, 1, 2], w)                 # beyond the last bin
     with pytest.raises(ValueError):
         DevicePixels(off, [0, 2], [5, 1], w)
+
+
+def test_random_block_layouts_match_c_oracle():
+    """k_px_assemble on arbitrary block tables (any order on the genome, reversed, overlapping, empty) against the
+    plain-C restatement; raw and balanced, NaN weights."""
+    from neoloopfinder_b200.scoring import DeviceAssembly, DevicePixels
+    from oracle import coracle as co
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        n = int(rng.integers(8, 300))
+        Cm = np.triu(rng.poisson(0.8, size=(n, n)))
+        w = rng.uniform(0.05, 0.2, n)
+        w[rng.random(n) < 0.1] = np.nan
+        rows, cols = np.nonzero(Cm)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=n), out=off[1:])
+        bin2, cnt = cols.astype(np.int32), Cm[rows, cols].astype(np.int32)
+        nblk = int(rng.integers(1, 6))
+        lo = rng.integers(0, n, size=nblk)
+        hi = np.minimum(n, lo + rng.integers(0, 80, size=nblk))
+        if int((hi - lo).sum()) == 0:
+            hi[0] = min(n, lo[0] + 3)
+        rev = rng.random(nblk) < 0.5
+        px = DevicePixels(off, bin2, cnt, w)
+        for balance in (True, False):
+            asm = DeviceAssembly.from_pixels(px, lo, hi, rev, balance=balance)
+            M, bias = co.assemble_pixels(off, bin2, cnt, w, lo, hi, rev, balance=balance)
+            assert np.array_equal(asm.fusion_matrix(), M), (trial, balance)
+            assert np.array_equal(asm.bias(), bias), (trial, balance)
+            asm.close()
+        px.close()
