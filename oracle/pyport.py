@@ -181,6 +181,158 @@ def linear_regression(exp1, exp2, min_samples=5):
     return rscores.max(), slopes[np.argmax(rscores)], warning
 
 
+# ----------------------------------------------------------------------------- callers.py:92-502, assembly.py:12-27
+class FusionPort:
+    """One SV as assemble-complexSVs analyses it (row f-3): matrix of the two flanks, induced-contact bounds,
+    slopes of the upstream / downstream / junction regions against the global expected."""
+
+    def __init__(self, clr, c1, c2, p1, p2, s1, s2, sv_type, span=5000000, col='sweight', trim=True, expected_values=None):
+        self.clr, self.res = clr, clr.binsize
+        self.p1, self.p2, self.s1, self.s2 = p1, p2, s1, s2
+        pre = 'chr' if list(clr.chromnames)[0].startswith('chr') else ''
+        self.c1, self.c2 = pre + c1.lstrip('chr'), pre + c2.lstrip('chr')
+        self.size1, self.size2 = clr.chromsizes[self.c1], clr.chromsizes[self.c2]
+        self.col = col
+        self.name = ','.join(map(str, [sv_type, c1.lstrip('chr'), p1, s1, c2.lstrip('chr'), p2, s2]))
+        self.expected = expected_values
+        self.get_matrix(span, col, trim)
+
+    def get_matrix(self, span, col, trim):
+        """callers.py:137-237: the four strand combinations, each with its intra-chromosomal special case."""
+        res, fetch = self.res, self.clr.matrix(balance=col).fetch
+        p1, p2, r = self.p1 // res, self.p2 // res, span // res
+        same = self.c1 == self.c2
+        mid = int((p2 - p1) / 2)
+        if self.s1 == '+' and self.s2 == '+':
+            lo2 = max(p2 - r, 0) if not same else (max(p2 - r, p1 + mid) if trim else max(p2 - r, p1 + 1))
+            k_p = [max(p1 - r, 0) * res, min(p1 * res + res, self.size1), min(p2 * res + res, self.size2), lo2 * res]
+            M1 = fetch((self.c1, k_p[0], k_p[1]))
+            M2 = fetch((self.c2, k_p[3], k_p[2]))[::-1, ::-1]
+            M3 = fetch((self.c1, k_p[0], k_p[1]), (self.c2, k_p[3], k_p[2]))[:, ::-1]
+        elif self.s1 == '+' and self.s2 == '-':
+            k_p = [max(p1 - r, 0) * res, min(p1 * res + res, self.size1), p2 * res, min((p2 + r + 1) * res, self.size2)]
+            M1 = fetch((self.c1, k_p[0], k_p[1]))
+            M2 = fetch((self.c2, k_p[2], k_p[3]))
+            M3 = fetch((self.c1, k_p[0], k_p[1]), (self.c2, k_p[2], k_p[3]))
+        elif self.s1 == '-' and self.s2 == '-':
+            if not same:
+                hi1 = min((p1 + r + 1) * res, self.size1)
+            elif trim:
+                hi1 = min((p1 + r + 1) * res, (p2 - mid) * res)
+            else:
+                hi1 = min((p1 + r + 1) * res, p2 * res - res)
+            k_p = [hi1, p1 * res, p2 * res, min((p2 + r + 1) * res, self.size2)]
+            M1 = fetch((self.c1, k_p[1], k_p[0]))[::-1, ::-1]
+            M2 = fetch((self.c2, k_p[2], k_p[3]))
+            M3 = fetch((self.c1, k_p[1], k_p[0]), (self.c2, k_p[2], k_p[3]))[::-1, :]
+        else:
+            if not same:
+                k_p = [min((p1 + r + 1) * res, self.size1), p1 * res, min(p2 * res + res, self.size2), max(p2 - r, 0) * res]
+            else:
+                k_p = [min(p1 + r + 1, p2 - mid - 1) * res, p1 * res, min(p2 * res + res, self.size2),
+                       max(p2 - r, p1 + mid + 1) * res]
+            M1 = fetch((self.c1, k_p[1], k_p[0]))[::-1, ::-1]
+            M2 = fetch((self.c2, k_p[3], k_p[2]))[::-1, ::-1]
+            M3 = fetch((self.c1, k_p[1], k_p[0]), (self.c2, k_p[3], k_p[2]))[::-1, ::-1]
+        n1, n = M1.shape[0], M1.shape[0] + M2.shape[0]
+        M = np.zeros((n, n))
+        M[:n1, :n1], M[n1:, n1:], M[:n1, n1:] = M1, M2, M3
+        M = np.triu(M)
+        if col:
+            M[np.isnan(M)] = 0
+        self.fusion_matrix, self.k_p, self.fusion_point = M, k_p, n1
+
+    def extract_bias(self, col):
+        """callers.py:240-262."""
+        k_p, parts = self.k_p, []
+        for c, a, b in ((self.c1, k_p[0], k_p[1]), (self.c2, k_p[2], k_p[3])):
+            t = self.clr.bins().fetch((c, min(a, b), max(a, b)))[col].values
+            if a > b:
+                t = t[::-1]
+            ok = np.logical_not((t == 0) | np.isnan(t))
+            wv = np.zeros_like(t)
+            wv[ok] = 1 / t[ok]
+            parts.append(wv)
+        self.bias = np.r_[parts[0], parts[1]]
+
+    @staticmethod
+    def _stretches(arr, min_seed_len=2, max_gap=1, min_stripe_len=5):
+        """callers.py:315-333."""
+        arr = np.sort(arr)
+        pieces = [p for p in np.split(arr, np.where(np.diff(arr) != 1)[0] + 1) if len(p) >= min_seed_len]
+        stripes, seed = [], pieces[0]
+        for p in pieces[1:]:
+            if p[0] - seed[-1] < max_gap + 2:
+                seed = np.r_[seed, p]
+            else:
+                if seed[-1] - seed[0] + 1 >= min_stripe_len:
+                    stripes.append([seed[0], seed[-1] + 1])
+                seed = p
+        if seed[-1] - seed[0] + 1 >= min_stripe_len:
+            stripes.append([seed[0], seed[-1] + 1])
+        return stripes
+
+    def _locate(self, pca1, left_most):
+        loci = sorted(self._stretches(np.where(pca1 >= 0)[0]) + self._stretches(np.where(pca1 <= 0)[0]))
+        return loci[0][1] - 1 if left_most else loci[-1][0]
+
+    def detect_bounds(self):
+        """callers.py:265-312."""
+        from scipy.ndimage import gaussian_filter
+        from sklearn.decomposition import PCA
+        n, junc = self.fusion_matrix.shape[0], self.fusion_point
+        self.up_i, self.down_i = 0, n - 1
+        inter = self.fusion_matrix[:junc, junc:]
+        rowmask, colmask = inter.sum(axis=1) != 0, inter.sum(axis=0) != 0
+        if rowmask.sum() >= 10 and colmask.sum() >= 10:
+            new = inter[rowmask][:, colmask]
+            try:
+                pca1 = PCA(n_components=3, whiten=True).fit_transform(gaussian_filter(np.corrcoef(new, rowvar=True), sigma=1))[:, 0]
+                self.up_i = np.where(rowmask)[0][self._locate(pca1, False)]
+            except Exception:       # noqa: BLE001
+                self.up_i = 0
+            try:
+                pca1 = PCA(n_components=3, whiten=True).fit_transform(gaussian_filter(np.corrcoef(new, rowvar=False), sigma=1))[:, 0]
+                self.down_i = np.where(colmask)[0][self._locate(pca1, True)] + junc
+            except Exception:       # noqa: BLE001
+                self.down_i = n - 1
+
+    def allele_slope(self):
+        """callers.py:415-478."""
+        self.extract_bias(self.col)
+        shape, p1L = self.fusion_matrix.shape, self.fusion_point
+        valid_bias = (self.bias[:, np.newaxis] * self.bias) > 0
+        for up_i, down_i in ((self.up_i, self.down_i), (0, self.bias.size - 1)):
+            best = []
+            for rows, cols in (((up_i, p1L), (up_i, p1L)), ((p1L, down_i), (p1L, down_i)), ((up_i, p1L), (p1L, down_i))):
+                mask = np.zeros(shape, dtype=bool)
+                mask[rows[0]:rows[1], cols[0]:cols[1]] = True
+                rs, ss = [], []
+                for maxdis in (200000, 400000, 500000, 1000000, 1500000, 2000000):
+                    r_, s_, _w = linear_regression(extract_xy(self.fusion_matrix, self.res, mask & valid_bias, maxdis=maxdis, mink=3),
+                                                   self.expected)
+                    rs.append(r_)
+                    ss.append(s_)
+                rs = np.r_[rs]
+                best.append((rs.max(), ss[rs.argmax()]))
+            (self.u_g_r, self.u_g_s), (self.d_g_r, self.d_g_s), (self.m_g_r, self.m_g_s) = best
+            if self.u_g_r > 0.6 and self.d_g_r > 0.6 and self.m_g_r > 0.6 and self.m_g_s > 0:
+                break
+
+    def correct_heterozygosity(self):
+        """callers.py:482-502."""
+        junc, hcm = self.fusion_point, self.fusion_matrix.copy()
+        self.u_s = self.d_s = 0
+        if self.u_g_r > 0.6 and self.d_g_r > 0.6:
+            slope, ms = max(self.u_g_s, self.d_g_s), min(self.u_g_s, self.d_g_s)
+            hcm[:junc, :junc] = hcm[:junc, :junc] / slope
+            hcm[junc:, junc:] = hcm[junc:, junc:] / slope
+            self.u_s, self.d_s = self.m_g_s / self.u_g_s, self.m_g_s / self.d_g_s
+            if self.m_g_r > 0.6 and self.m_g_s / ms > 0.1:
+                hcm[self.up_i:junc, junc:self.down_i] = hcm[self.up_i:junc, junc:self.down_i] * min(1 / self.m_g_s, 5 / slope)
+        self.hcm = hcm
+
+
 # ----------------------------------------------------------------------------- assembly.py:278-596
 class AssemblyPort:
     def __init__(self, clr, candidate, span=5000000, col='sweight', flexible=True, slopes={}, expected_values=None):

@@ -85,3 +85,27 @@ def test_port_matches_live_reference():
     ref = cli.pipeline(clr, "C9", {"C9": line}, 600000, "sweight", 0.3, 2, False, model, exp_ref)
     got = pyport.pipeline(clr, "C9", {"C9": line}, 600000, "sweight", 0.3, 2, False, model, exp_port)
     assert ref == got and len(ref) > 0
+
+
+def test_fusion_port_matches_the_reference_fixture():
+    """Row f-3: the port of Fusion (matrix, bounds, slopes, rescaled matrix) against the fixture the REAL reference
+    wrote for every SV of the assemble-complexSVs workload (tests/golden/assemble_10k.json)."""
+    import hashlib
+    import json
+    from neoloopfinder_b200.coolshim import SyntheticCooler
+    from oracle import pyport
+    z = json.load(open(os.path.join(GOLDEN, "assemble_10k.json")))
+    clr = SyntheticCooler.from_spec(z["cooler_spec"])
+    expected = {i: v for i, v in enumerate(z["expected"])}
+    for want in z["per_sv"]:
+        note, c1, p1, s1, c2, p2, s2 = want["name"].split(",")
+        fu = pyport.FusionPort(clr, c1, c2, int(p1), int(p2), s1, s2, note, span=z["span"], col=z["col"], trim=False,
+                               expected_values=expected)
+        fu.detect_bounds()
+        fu.allele_slope()
+        fu.correct_heterozygosity()
+        assert fu.name == want["name"] and [int(v) for v in fu.k_p] == want["k_p"]
+        assert (int(fu.up_i), int(fu.down_i)) == (want["up_i"], want["down_i"])
+        for k in ("u_g_r", "u_g_s", "d_g_r", "d_g_s", "m_g_r", "m_g_s", "u_s", "d_s"):
+            assert float(getattr(fu, k)) == want[k], (fu.name, k)
+        assert hashlib.sha256(np.ascontiguousarray(fu.hcm).tobytes()).hexdigest() == want["hcm_sha"]
