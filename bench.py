@@ -4,13 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
     python bench.py --impl reference ...                     (CPU arm: the oracle port of the reference)
 
-Workload (BASELINE.json configs[1]): a synthetic 10 kb hg38-sized contact map with 50 simple
-translocation / deletion / inversion assemblies per GPU, 3 Mb span.  A "step" is one pass of the
-scoring path -- host gap-free matrix in -> called loops out: per-diagonal means +
-isotonic expected, candidate gate, window features, forest, threshold, pooling -- over the whole
-batch.  ``value`` times it with the matrices already resident in HBM; ``e2e`` times the public
-call ``score_matrices`` with HOST (pinned) matrices, host->device copies and result read-back
-inside the timed region.  Weak scaling: every rank scores its own 50 assemblies (different seeds).
+Default workload = the configuration BASELINE.json's metric is quoted on (configs[2], "cfg3"): a synthetic
+5 kb hg38-sized contact map with 192 complex assemblies (chains of 2-5 SVs, 3-6 blocks, 1.2-4 k bins each),
+3 Mb span.  The list is FIXED: under torchrun the product's own sharder (``sharding.shard_ids``, greedy LPT
+on estimated pixels) deals it to the ranks, so 1 -> 8 GPUs is STRONG scaling of one job.  The rank's part
+of the sample lives in a pixel table (cooler's layout) resident in HBM; assemblies are built, normalised and
+gap-filtered from it by the product path (SURVEY.md section 8 rows a-C .. a-E, f-2).
+
+A "step" is one pass of the scoring path -- gap-free matrix in -> called loops out:
+per-diagonal means + isotonic expected, candidate gate, window features, forest, threshold, pooling -- over
+the rank's whole shard.  ``value`` times it with the matrices already resident in HBM; ``e2e`` times the
+public call ``score_matrices`` with HOST (pinned) matrices, host->device copies and result read-back inside
+the timed region.  ``cli_e2e`` is the wall time of the product entry ``call_assemblies`` (what
+``neoloop-caller`` runs per resolution) on the same shard: matrix assembly from the pixel table, diagonal
+means, every host regression, scoring, pooling and coordinate bookkeeping.  ``parity`` compares, in the
+same run, the GPU results with the CPU port of the reference on the sample the CPU baseline is timed on.
 """
 from __future__ import annotations
 
@@ -30,132 +38,121 @@ if ROOT not in sys.path:
 
 METRIC = "candidate pixels scored/sec"
 UNIT = "pixels/s"
-RES = 10000
 SPAN = 3_000_000
-N_ASSEMBLIES = 50
 THRESHOLD = 0.9
-KIND = "simple"             # synth.make_workload kind: 'simple' (cfg2) or 'complex' (cfg3)
-WORKLOAD = "cfg2"
+SEED = 100
 MODEL = os.path.join(ROOT, "tests", "golden", "forest_w6.joblib")
+WORKLOADS = {
+    # name: (resolution, synth kind, total assemblies, description)
+    "cfg3": (5000, "complex", 192, "cfg3 (BASELINE.json configs[2]): synthetic 5 kb hg38-sized map, %d complex assemblies "
+                                   "(chains of 2-5 SVs) in total"),
+    "cfg2": (10000, "simple", 50, "cfg2 (BASELINE.json configs[1]): synthetic 10 kb hg38-sized map, %d simple SV assemblies in total"),
+}
+CROP = 700              # bins of a parity / CPU-baseline matrix (about 15-20 s of one core per matrix at 5 kb)
+CPU_SLICE = 50000       # candidates per work unit of the reference arm (about 13 s of one core)
 
 
-def select_workload(name, n_assemblies):
-    """cfg2 (default, BASELINE.json configs[1]): 10 kb, simple SV assemblies.  cfg3 (configs[2]): 5 kb, complex
-    multi-breakpoint assemblies (2-5 chained SVs, 3-6 blocks, 1.2-4 k bins each); fewer of them per GPU because
-    the untimed host preparation fetches every block pair from the procedural map."""
-    global RES, KIND, WORKLOAD, N_ASSEMBLIES
-    WORKLOAD = name
-    if name == "cfg3":
-        RES, KIND = 5000, "complex"
-    N_ASSEMBLIES = n_assemblies if n_assemblies else (24 if name == "cfg3" else 50)
-    return N_ASSEMBLIES
+class Workload:
+    def __init__(self, name, n_assemblies):
+        self.name = name
+        self.res, self.kind, default_n, self.what = WORKLOADS[name]
+        self.n = n_assemblies or default_n
+
+    def build(self):
+        from neoloopfinder_b200.synth import analytic_expected, make_workload
+        clr, lines = make_workload(self.kind, res=self.res, seed=SEED, n_assemblies=self.n, span=SPAN)
+        return clr, lines, analytic_expected(clr)
+
+    def config(self, n_gpus):
+        return {
+            "workload": "%s, 3 Mb span, prob %.2f" % (self.what % self.n, THRESHOLD),
+            "resolution": self.res, "assemblies_total": self.n, "span_bp": SPAN,
+            "forest": "synthetic sklearn RandomForest, 100 trees, depth<=20, 32048 nodes, 169 features (tests/golden/forest_w6.joblib)",
+            "expected": "analytic A/(d+1) of the procedural map",
+            "source": "regional pixel table (cooler layout) resident in HBM; assemblies built on the device",
+            "sharding": ("one fixed assembly list dealt to %d ranks by sharding.shard_ids (LPT on estimated pixels), "
+                         "one process per GPU, no collective on the data path" % n_gpus) if n_gpus > 1 else "single GPU",
+            "cache": "L2 flushed (256 MB memset) at the start of every step",
+        }
 
 
-def workload_config(n_gpus):
-    what = ("cfg2: synthetic 10 kb hg38-sized map, %d simple SV assemblies per GPU" if WORKLOAD == "cfg2" else
-            "cfg3: synthetic 5 kb hg38-sized map, %d complex (2-5 chained SVs) assemblies per GPU") % N_ASSEMBLIES
-    return {
-        "workload": "%s, 3 Mb span, prob %.2f" % (what, THRESHOLD),
-        "resolution": RES, "assemblies_per_gpu": N_ASSEMBLIES, "span_bp": SPAN,
-        "forest": "synthetic sklearn RandomForest, 100 trees, depth<=20, 32048 nodes, 169 features (tests/golden/forest_w6.joblib)",
-        "expected": "analytic A/(d+1) of the procedural map",
-        "sharding": "by assembly, one process per GPU, no collective on the data path" if n_gpus > 1 else "single GPU",
-        "cache": "L2 flushed (256 MB memset) at the start of every step",
-    }
+def gap_free_matrices(clr, ids, lines, expected, ctx, forest, res, nproc=1):
+    """Untimed preparation with the product path (cli.call_assemblies: assemble, normalise, remove gaps):
+    -> (gap-free host matrices, block id per gap-free bin) of the valid assemblies, in list order."""
+    from neoloopfinder_b200.cli import call_assemblies
+    collected = {}
+    call_assemblies(clr, ids, lines, SPAN, "sweight", THRESHOLD, 2, False, forest, expected, ctx, nproc=nproc,
+                    collect=collected)
+    order = [ID for ID in ids if ID in collected]
+    return [collected[ID][0] for ID in order], [collected[ID][1] for ID in order]
 
 
 # --------------------------------------------------------------------------------------------
-def build_assemblies(rank, n_asm):
-    from neoloopfinder_b200.synth import analytic_expected, make_workload
-    clr, lines = make_workload(KIND, res=RES, seed=100 + rank, n_assemblies=n_asm, span=SPAN)
-    expected = analytic_expected(clr)
-    return clr, lines, expected
-
-
-def gap_free_matrices_gpu(clr, lines, expected, ctx):
-    """Untimed preparation with the product path: assemble, normalise, remove gaps."""
-    from neoloopfinder_b200.assembly import complexSV
-    mats, chains = [], []
-    for ID, line in lines.items():
-        fu = complexSV(clr, line, span=SPAN, col="sweight", expected_values=expected, flexible=False)
-        fu.reorganize_matrix()
-        if len(fu.Map) != fu.fusion_matrix.shape[0]:
-            continue
-        fu._ctx = ctx
-        fu.correct_heterozygosity()
-        fu.remove_gaps()
-        asm = fu._device_assembly()
-        G = asm.gap_free()
-        chain_of = np.array([fu.chains[k] for k in range(fu.fusion_matrix.shape[0])])
-        chains.append(chain_of[asm.kept_index()])
-        mats.append(G)
-        asm.close()
-    return mats, chains
-
-
-def gap_free_matrices_cpu(clr, lines, expected, limit):
-    """Same preparation with the oracle port (CPU arm)."""
+# CPU side (oracle port): only the cpu_baseline leg and the reference arm come here
+# --------------------------------------------------------------------------------------------
+def _cpu_score_whole(args):
+    """The reference's scoring path (Peakachu init, candidates, getwindow, predict_proba, threshold,
+    pooling) on one whole gap-free matrix -> (clist, probas, sorted loop list)."""
+    G, chains, expected, model_path, thre, res = args
     from oracle import pyport
-    out = []
-    for ID, line in list(lines.items())[:limit]:
-        fu = pyport.AssemblyPort(clr, line, span=SPAN, col="sweight", expected_values=expected, flexible=False)
-        fu.reorganize_matrix()
-        if len(fu.Map) != fu.fusion_matrix.shape[0]:
-            continue
-        fu.correct_heterozygosity()
-        fu.remove_gaps()
-        out.append((fu.gap_free, fu.index_map, fu.chains))
-    return out
+    core = pyport.PeakachuPort(G, upper=400 * res, res=res)
+    core.load_expected(expected)
+    core.load_models(model_path)
+    cap = {}
+    loops = core.predict(thre=thre, no_pool=False, min_count=2, index_map=None, chains=chains, capture=cap)
+    clist = np.asarray(cap.get("clist", np.zeros((0, 2))), dtype=np.int64).reshape(-1, 2)
+    probas = np.asarray(cap.get("probas", np.zeros(0)), dtype=np.float64)
+    return clist, probas, sorted((int(i), int(j)) for i, j, _p in loops)
 
 
 _CPU_CORES = {}      # per worker process: matrix -> (PeakachuPort, all candidate rows, all candidate columns)
 
 
-def _cpu_score_one(args):
-    """The reference's scoring path (Peakachu init, candidates, getwindow, predict_proba, pooling)
-    on one gap-free matrix, restricted to one slice of its candidate list.  The per-matrix set-up
-    (CSR, candidates, model load: once per ~150 k candidates in the reference) is kept per worker
+def _cpu_score_slice(args):
+    """Same path restricted to one slice of the matrix's candidate list (reference arm).  The per-matrix
+    set-up (CSR, candidates, model load: once per ~200 k candidates in the reference) is kept per worker
     process, so short slices measure the same per-pixel rate as whole matrices."""
-    G, index_map, chains, expected, model_path, lo, hi, thre = args
+    G, chains, expected, model_path, lo, hi, thre, res = args
     from oracle import pyport
     key = (G.shape[0], float(G[::5, ::5].sum()), model_path)
     if key not in _CPU_CORES:
-        core = pyport.PeakachuPort(G, upper=400 * RES, res=RES)
+        core = pyport.PeakachuPort(G, upper=400 * res, res=res)
         core.load_expected(expected)
         core.load_models(model_path)
         _CPU_CORES[key] = (core, core.ridx, core.cidx)
     core, ridx, cidx = _CPU_CORES[key]
     core.ridx, core.cidx = ridx[lo:hi], cidx[lo:hi]
     cap = {}
-    core.predict(thre=thre, no_pool=False, min_count=2, index_map=index_map, chains=chains, capture=cap)
+    core.predict(thre=thre, no_pool=False, min_count=2, index_map=None, chains=chains, capture=cap)
     return int(cap.get("n_scored", 0))
 
 
-CPU_SLICE = 50000      # candidates per work unit (about 13 s of one core)
+def _cpu_prepare(args):
+    """Assembly -> gap-free matrix with the oracle port (reference arm)."""
+    clr, line, expected = args
+    from oracle import pyport
+    fu = pyport.AssemblyPort(clr, line, span=SPAN, col="sweight", expected_values=expected, flexible=False)
+    fu.reorganize_matrix()
+    if len(fu.Map) != fu.fusion_matrix.shape[0]:
+        return None
+    fu.correct_heterozygosity()
+    fu.remove_gaps()
+    n = fu.fusion_matrix.shape[0]
+    chain_of = np.array([fu.chains[k] for k in range(n)])
+    kept = np.array([fu.index_map[k] for k in range(len(fu.index_map))], dtype=np.int64)
+    return np.ascontiguousarray(fu.gap_free), chain_of[kept]
 
 
-def cpu_work_units(items, expected, n_units, cpu_slice=CPU_SLICE):
-    """(matrix, candidate slice) units: unit k takes slice k // n_items of matrix k % n_items."""
-    units = []
-    for k in range(n_units):
-        G, im, ch = items[k % len(items)]
-        s = k // len(items)
-        units.append((G, im, ch, expected, MODEL, s * cpu_slice, (s + 1) * cpu_slice, THRESHOLD))
-    return units
-
-
-def cpu_reference_rate(items, expected, workers, n_units=None, cpu_slice=CPU_SLICE):
-    """pixels/s of the oracle port over `workers` loky processes (the reference fans out the same
-    way, scripts/neoloop-caller:159)."""
-    from joblib import Parallel, delayed
-    units = cpu_work_units(items, expected, n_units or workers, cpu_slice)
-    t0 = time.perf_counter()
-    if workers == 1:
-        scored = [_cpu_score_one(u) for u in units]
-    else:
-        scored = Parallel(n_jobs=workers)(delayed(_cpu_score_one)(u) for u in units)
-    dt = time.perf_counter() - t0
-    return sum(scored) / dt, sum(scored), dt
+def crop_matrix(G, chains, size=CROP):
+    """A size x size diagonal sub-matrix around the first junction of the assembly (upper triangular like
+    its parent): the unit of the parity check and of the CPU baseline."""
+    n = G.shape[0]
+    if n <= size:
+        return np.ascontiguousarray(G), np.asarray(chains)
+    cuts = np.flatnonzero(np.diff(np.asarray(chains)))
+    j = int(cuts[0]) + 1 if len(cuts) else n // 2
+    a = int(min(max(0, j - size // 2), n - size))
+    return np.ascontiguousarray(G[a:a + size, a:a + size]), np.asarray(chains)[a:a + size]
 
 
 class ClockSampler:
@@ -218,34 +215,56 @@ def n_band_cells(n, upper=400, w=7):
     return int((n - d).sum())
 
 
+def dense_upload_bytes(n, bw=414):
+    """Bytes nlf_batch_add_dense moves host -> device for an n x n matrix (csrc/score.cu): everything below
+    1024 bins, else per block of 128 rows only the columns k_bandify reads."""
+    if n < 1024:
+        return 8 * n * n
+    total = 0
+    for r0 in range(0, n, 128):
+        r1 = min(n, r0 + 128)
+        total += 8 * (min(n, r1 - 1 + bw) - max(0, r0 - 13)) * (r1 - r0)
+    return total
+
+
 # --------------------------------------------------------------------------------------------
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, wl, rank):
     """CPU arm: the oracle port (the reference tree does not travel to the GPU box) on all host
     cores, each step a bounded sample of the same workload."""
     if rank != 0:
         return
+    from joblib import Parallel, delayed
     cores = os.cpu_count() or 1
-    clr, lines, expected = build_assemblies(0, N_ASSEMBLIES)
-    items = gap_free_matrices_cpu(clr, lines, expected, 6)
-    workers = min(cores, 3 * len(items))           # a 10 kb assembly has ~3 slices of CPU_SLICE candidates
+    clr, lines, expected = wl.build()
+    n_mats = 4 if wl.name == "cfg3" else 6
+    todo = [(clr, ln, expected) for ln in list(lines.values())[:n_mats + 2]]
+    prepared = Parallel(n_jobs=min(cores, len(todo)))(delayed(_cpu_prepare)(t) for t in todo)
+    items = [p for p in prepared if p is not None][:n_mats]
+    per_matrix = 4 if wl.name == "cfg3" else 3          # slices of CPU_SLICE candidates a matrix offers
+    workers = min(cores, per_matrix * len(items))
     if args.warmup > 0:
-        from joblib import Parallel, delayed
         Parallel(n_jobs=workers)(delayed(int)(k) for k in range(workers))       # start the loky workers
     # bounded sample: a step is one work unit per worker; the slice shrinks with --steps so that the whole
     # run stays near three minutes whatever K the caller asks for (about 0.26 ms of one core per candidate)
     cpu_slice = int(min(CPU_SLICE, max(6000, CPU_SLICE * 14 // max(1, args.steps))))
     pix, secs = 0, 0.0
     for _ in range(args.steps):
-        r, p, dt = cpu_reference_rate(items, expected, workers, cpu_slice=cpu_slice)
-        pix += p
-        secs += dt
+        units = []
+        for k in range(workers):
+            G, ch = items[k % len(items)]
+            s = k // len(items)
+            units.append((G, ch, expected, MODEL, s * cpu_slice, (s + 1) * cpu_slice, THRESHOLD, wl.res))
+        t0 = time.perf_counter()
+        scored = Parallel(n_jobs=workers)(delayed(_cpu_score_slice)(u) for u in units)
+        secs += time.perf_counter() - t0
+        pix += sum(scored)
     value = pix / secs
     sample = ("%d work units per step = %d assemblies x candidate slices of %d, oracle/pyport.py, joblib loky n_jobs=%d"
               % (workers, len(items), cpu_slice, workers))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -256,21 +275,22 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--assemblies", type=int, default=0, help="assemblies per GPU (default: 50 for cfg2, 24 for cfg3)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--assemblies", type=int, default=0, help="assemblies in TOTAL (default: 192 for cfg3, 50 for cfg2)")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the cli_e2e measurement")
     args = ap.parse_args()
-    args.assemblies = select_workload(args.workload, args.assemblies)
+    wl = Workload(args.workload, args.assemblies)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, wl, rank)
         return
 
     import torch
@@ -282,32 +302,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.cli import call_assemblies
     from neoloopfinder_b200.forest import load_forest
     from neoloopfinder_b200.scoring import ScoreBatch, score_and_pool, score_matrices
-
-    ctx = _lib.Context.get(local_rank)
-    forest = load_forest(MODEL, ctx)
-    clr, lines, expected = build_assemblies(rank, args.assemblies)
-    exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
-    mats, chains = gap_free_matrices_gpu(clr, lines, expected, ctx)
-    # pinned host copies for the end-to-end arm
-    pinned = [torch.from_numpy(G).pin_memory() for G in mats]
-    host_mats = [t.numpy() for t in pinned]
-    h2d_bytes = int(sum(G.nbytes for G in host_mats))
-
-    resident = ScoreBatch(4, 400, ctx)
-    for G in host_mats:
-        resident.add_dense(G)
-    ctx.sync()
-
-    def step_resident():
-        ctx.l2_flush()
-        resident.reset()
-        return score_and_pool(resident, forest, exp_arr, THRESHOLD, RES, 2, chains, False)
-
-    def step_e2e():
-        ctx.l2_flush()
-        return score_matrices(host_mats, forest, exp_arr, THRESHOLD, RES, 2, chains, False, 400, ctx)
+    from neoloopfinder_b200.sharding import shard_ids
+    from neoloopfinder_b200.synth import regional_pixel_cooler
 
     def barrier():
         ctx.sync()
@@ -315,19 +314,72 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce(x, dist.ReduceOp.MAX)
+
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce(x, dist.ReduceOp.SUM)
+
+    cores = os.cpu_count() or 1
+    nproc = max(1, cores // world)
+    ctx = _lib.Context.get(local_rank)
+    forest = load_forest(MODEL, ctx)
+    t_prep = time.perf_counter()
+    clr_syn, lines, expected = wl.build()
+    ids = list(lines)
+    mine = shard_ids(ids, lines, SPAN, wl.res, world)[rank]            # the product's sharder, one fixed list
+    my_lines = {ID: lines[ID] for ID in mine}
+    clr = regional_pixel_cooler(clr_syn, my_lines, SPAN, nproc=nproc)   # this rank's part of the sample, cooler layout
+    exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
+    table_s = time.perf_counter() - t_prep
+
+    # ---- the product entry on this shard: warm (pixel table upload, loky workers), then timed wall clock
+    cli = None
+    call_assemblies(clr, mine[:2], lines, SPAN, "sweight", THRESHOLD, 2, False, forest, expected, ctx, nproc=nproc)
+    if not args.no_cli:
+        st = {}
+        barrier()
+        t0 = time.perf_counter()
+        res_cli = call_assemblies(clr, mine, lines, SPAN, "sweight", THRESHOLD, 2, False, forest, expected, ctx, st, nproc)
+        ctx.sync()
+        my_cli = time.perf_counter() - t0
+        barrier()
+        cli_s = max_over_ranks(my_cli)
+        cli = {"seconds": cli_s, "assemblies": wl.n, "scored_pixels": int(sum_over_ranks(float(st.get("scored", 0)))),
+               "loops": int(sum_over_ranks(float(sum(len(r) for r in res_cli.values() if r)))),
+               "host_workers_per_gpu": nproc,
+               "what": "wall time of cli.call_assemblies on every rank's shard (max over ranks): assembly from the resident "
+                       "pixel table, diagonal means, host Huber/isotonic regressions on loky workers, scoring, pooling, "
+                       "coordinates; the pixel table upload is outside"}
+        cli["pixels_per_s"] = cli["scored_pixels"] / cli_s if cli_s > 0 else None
+    # ---- untimed preparation with the same product path, keeping the gap-free matrices on the host
+    mats, chains = gap_free_matrices(clr, mine, lines, expected, ctx, forest, wl.res, nproc)
+    pinned = [torch.from_numpy(G).pin_memory() for G in mats]
+    host_mats = [t.numpy() for t in pinned]
+    del mats
+    h2d_bytes = int(sum(dense_upload_bytes(G.shape[0]) for G in host_mats))
+
+    resident = ScoreBatch(4, 400, ctx)
+    for G in host_mats:
+        resident.add_dense(G)
+    ctx.sync()
+    prep_s = time.perf_counter() - t_prep
+
+    def step_resident():
+        ctx.l2_flush()
+        resident.reset()
+        return score_and_pool(resident, forest, exp_arr, THRESHOLD, wl.res, 2, chains, False)
+
+    def step_e2e():
+        ctx.l2_flush()
+        return score_matrices(host_mats, forest, exp_arr, THRESHOLD, wl.res, 2, chains, False, 400, ctx)
 
     # ---- resident (kernel-path) measurement
     sampler = ClockSampler(local_rank)
@@ -347,12 +399,12 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
-    ms = ctx.timer_stop()
+    ms_mine = max(ctx.timer_stop(), 0.0)
     barrier()
     wall_ms = 1000.0 * (time.perf_counter() - t0)
     launches = sum_over_ranks(float(ctx.launch_count() - launches0))      # whole job, like `value`
     mark1 = sampler.mark()
-    ms = max_over_ranks(max(ms, 0.0))
+    ms = max_over_ranks(ms_mine)
     total_scored = sum_over_ranks(float(scored_per_step)) * args.steps
     value = total_scored / (ms * 1e-3)
     prof = {k: ctx.profile_read(v) for k, v in _lib.PROF.items()}
@@ -365,20 +417,28 @@ def main():
     ctx.timer_start()
     t_e2e = time.perf_counter()
     for _ in range(args.steps):
-        t_dbg = time.perf_counter()
-        loops_e, counts_e = step_e2e()
-        if os.environ.get("NLF_BENCH_DEBUG"):
-            print("e2e step %.2f ms" % (1e3 * (time.perf_counter() - t_dbg)), file=sys.stderr)
-    ms_e = ctx.timer_stop()
+        step_e2e()
+    ms_e_mine = ctx.timer_stop()
     wall_e = 1000.0 * (time.perf_counter() - t_e2e)
     barrier()
-    ms_e = max_over_ranks(ms_e)
+    ms_e = max_over_ranks(ms_e_mine)
     clocks = sampler.stop(mark0, mark1)
     e2e_value = total_scored / (ms_e * 1e-3)
-    d2h_bytes = int(24 * donuts_per_step + 3 * 8 * len(host_mats) + donuts_per_step)
+    d2h_mine = int(25 * donuts_per_step + 3 * 8 * len(host_mats))
+    h2d_total = int(sum_over_ranks(float(h2d_bytes)))
+    d2h_total = int(sum_over_ranks(float(d2h_mine)))
+
+    # per-rank table (strong scaling: the slowest rank sets the pace)
+    per_rank = None
+    if world > 1:
+        mine_t = torch.tensor([float(len(host_mats)), float(scored_per_step), ms_mine / args.steps, ms_e_mine / args.steps,
+                               my_cli if cli else 0.0], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        per_rank = [{"rank": r, "assemblies": int(t[0]), "scored_per_step": int(t[1]), "ms_per_step": float(t[2]),
+                     "e2e_ms_per_step": float(t[3]), "cli_seconds": float(t[4])} for r, t in enumerate(allt)]
 
     if rank == 0:
-        # ---- roofline of the dominant kernel
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -386,91 +446,131 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
         nband = sum(n_band_cells(G.shape[0]) for G in host_mats)
-        alg_bytes = 8.0 * nband + 16.0 * scored_per_step            # SURVEY.md section 8(d), fused K5-K9
+        alg_bytes = 8.0 * nband + 16.0 * scored_per_step            # SURVEY.md section 8(d), fused K5-K9, this rank
         kern = {}
         for k, (tms, n) in prof.items():
             if n:
                 kern[k] = {"ms_per_step": tms / args.steps, "launches_per_step": n / args.steps}
-        # dominant kernel = the longest single launch: k_features (one launch per step; the forest runs as
-        # 2 part launches + the NaN clean-up).  achieved = algorithmic bytes of the fused scoring path
-        #  / that launch's CUDA-event duration.
-        feat_ms = prof["feature"][0] / max(1, prof["feature"][1])
+        feat_ms = prof["feature"][0] / max(1, args.steps)
         forest_ms = prof["forest"][0] / max(1, args.steps)
-        achieved = alg_bytes / (feat_ms * 1e-3) / 1e9
+        score_ms = prof["score"][0] / max(1, args.steps) if "score" in prof else 0.0
+        # the dominant kernel by time: forest traversal (LSU / shared-memory bound), features (fp64-issue bound)
+        # or, when the two run concurrently on the same SMs, the overlapped pair timed as one region
+        if score_ms > 0:
+            dom, dom_ms = "k_features || k_forest_one (co-resident on every SM, timed together)", score_ms
+        elif forest_ms >= feat_ms:
+            dom, dom_ms = "k_forest", forest_ms
+        else:
+            dom, dom_ms = "k_features", feat_ms
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
         fp64_peak = ctx.fp64_peak_gops()
         alg_ops = 4940.0 * scored_per_step                           # add/mul + div per pixel
         band_bytes = 8.0 * sum(G.shape[0] * 416 for G in host_mats)
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if WORKLOAD == "cfg2" and tr.get("assemblies") == args.assemblies and tr.get("kernel") == "k_features":
-                traffic = tr["dram_bytes_per_launch"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if tr.get("workload") == wl.name and tr.get("assemblies") == len(host_mats):
+                traffic = tr["dram_bytes_per_step"]
         except (OSError, ValueError, KeyError):
             pass
         roofline = {
-            "bound": "hbm", "kernel": "k_features",
+            "bound": "hbm", "kernel": dom,
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
-            "launch_ms": feat_ms,
-            "note": "k_features is fp64-issue bound and the forest kernel shared-memory bound by construction "
-                    "(SURVEY.md D7: ~29 B but ~5k fp64 ops per pixel), so the HBM fraction on algorithmic bytes is small; "
-                    "the fp64-issue fraction is in roofline_fp64. traffic (ncu dram bytes, profiles/r01_traffic.json) exceeds the "
-                    "algorithmic bytes because the float32 features (676 B/pixel) go through HBM between k_features and the "
-                    "forest kernel.",
+            "launch_ms": dom_ms,
+            "note": "The contract's HBM fraction on ALGORITHMIC bytes (8*N_band + 16*N_scored, SURVEY.md 8d) for the dominant "
+                    "kernel(s).  It is small by construction (SURVEY.md D7: ~29 B but ~5k fp64 ops and ~1600 tree-node visits "
+                    "per pixel): the binding resources are the fp64 pipe (roofline_fp64) and the shared-memory wavefront "
+                    "rate (roofline_smem); the HBM-bound band kernels are in roofline_band.",
         }
         fp64 = {
             "kernel": "k_features", "achieved_gops": alg_ops / (feat_ms * 1e-3) / 1e9 if feat_ms else None,
             "peak_gops": fp64_peak, "peak_source": "DADD/DMUL issue micro-benchmark in this run (no FMA)",
             "frac": (alg_ops / (feat_ms * 1e-3) / 1e9) / fp64_peak if feat_ms else None,
             "algorithmic_ops_per_pixel": 4940,
+            "note": "feature kernel timed over its own launches; when it shares the SMs with the forest kernel its "
+                    "launch time includes the slowdown from sharing",
         }
-        forest_info = {
-            "kernel": "k_forest_pipe<32 warps, 2 trees per lane> x parts + k_forest_nan", "ms_per_step": forest_ms,
-            "node_visits_per_s": 1617.0 * scored_per_step / (forest_ms * 1e-3) if forest_ms else None,
-            # shared-memory roofline of the traversal: a warp node step needs at least 3 wavefronts (one
-            # conflict-free 4-byte feature load + one 8-byte node load = two 128-byte wavefronts); an SM
-            # serves one wavefront per clock
-            "smem_roofline": ({
-                "algorithmic_wavefronts_per_step": 3.0 * 1617.0 * scored_per_step / 32.0,
-                "achieved_gwavefronts_per_s": 3.0 * 1617.0 * scored_per_step / 32.0 / (forest_ms * 1e-3) / 1e9,
-                "peak_gwavefronts_per_s": 148 * 1.965,
-                "frac": 3.0 * 1617.0 * scored_per_step / 32.0 / (forest_ms * 1e-3) / 1e9 / (148 * 1.965),
-                "peak_source": "148 SMs x 1.965 GHz (MEASURED_PEAKS.json sm_max_mhz) x 1 wavefront per clock",
-            } if forest_ms else None),
-            "note": "about 1617 node visits per pixel (100 trees, mean leaf depth 16.2); bound by shared-memory "
-                    "wavefronts and issue slots, see profiles/r01_ncu_summary.md",
+        visits = forest.visits_per_pixel if hasattr(forest, "visits_per_pixel") else 1617.0
+        wf = 3.0 * visits * scored_per_step / 32.0
+        smem = {
+            "kernel": "k_forest", "ms_per_step": forest_ms,
+            "node_visits_per_s": visits * scored_per_step / (forest_ms * 1e-3) if forest_ms else None,
+            "algorithmic_wavefronts_per_step": wf,
+            "achieved_gwavefronts_per_s": wf / (forest_ms * 1e-3) / 1e9 if forest_ms else None,
+            "peak_gwavefronts_per_s": 148 * sm_mhz * 1e-3,
+            "frac": wf / (forest_ms * 1e-3) / 1e9 / (148 * sm_mhz * 1e-3) if forest_ms else None,
+            "peak_source": "148 SMs x sm_max_mhz (MEASURED_PEAKS.json) x 1 shared-memory wavefront per clock",
+            "note": "a warp node step needs >= 3 wavefronts (4-byte feature load + 8-byte node load); %.0f node visits "
+                    "per pixel on this forest" % visits,
         }
-        kern_tab = {}
-        for k, v in kern.items():
-            kern_tab[k] = dict(v)
-        if "diag" in kern_tab:
-            kern_tab["diag"]["hbm_gbs"] = band_bytes / (kern_tab["diag"]["ms_per_step"] * 1e-3) / 1e9
+        band = {}
+        for k in ("diag", "threshold", "bandify"):
+            if k in kern and kern[k]["ms_per_step"] > 0:
+                nbytes = band_bytes * (2.0 if k == "bandify" else 1.0)
+                band[k] = {"ms_per_step": kern[k]["ms_per_step"], "bytes_per_step": nbytes,
+                           "hbm_gbs": nbytes / (kern[k]["ms_per_step"] * 1e-3) / 1e9,
+                           "frac": nbytes / (kern[k]["ms_per_step"] * 1e-3) / 1e9 / hbm_peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": wl.config(world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
+                    "ms_per_step": ms_e / args.steps, "wall_ms_per_step_rank0": wall_e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_fp64": fp64, "forest": forest_info, "kernels": kern_tab,
-            "pixels": {"scored_per_step_rank0": scored_per_step, "candidates_per_step_rank0": cand_per_step,
-                       "donuts_per_step_rank0": donuts_per_step, "loops_per_step_rank0": n_loops,
-                       "band_cells_rank0": nband},
-            "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": roofline, "roofline_fp64": fp64, "roofline_smem": smem, "roofline_band": band, "kernels": kern,
+            "pixels": {"scored_per_step_total": int(total_scored / args.steps), "scored_per_step_rank0": scored_per_step,
+                       "candidates_per_step_rank0": cand_per_step, "donuts_per_step_rank0": donuts_per_step,
+                       "loops_per_step_rank0": n_loops, "band_cells_rank0": nband, "assemblies_rank0": len(host_mats)},
+            "wall_ms_per_step_rank0": wall_ms / args.steps,
+            "prep_seconds_rank0": {"pixel_table": table_s, "total_before_timing": prep_s},
         }
+        if cli:
+            line["cli_e2e"] = cli
+        if per_rank:
+            line["per_rank"] = per_rank
         if not args.no_cpu_baseline and world == 1:                   # reported at N=1 only
-            cores = os.cpu_count() or 1
-            items = [(G, None, ch) for G, ch in zip(host_mats[:8], chains[:8])]
-            workers = min(cores, 3 * len(items))
-            rate, pix, secs = cpu_reference_rate(items, expected, workers)
+            from joblib import Parallel, delayed
+            workers = min(cores, 16, len(host_mats))
+            picks = [int(round(k * (len(host_mats) - 1) / max(1, workers - 1))) for k in range(workers)]
+            crops = [crop_matrix(host_mats[k], chains[k]) for k in picks]
+            # GPU on the very same matrices (public batch API), outside every timed region
+            pb = ScoreBatch(4, 400, ctx)
+            for G, _ch in crops:
+                pb.add_dense(G)
+            g_loops, _cnt = score_and_pool(pb, forest, exp_arr, THRESHOLD, wl.res, 2, [ch for _G, ch in crops], False)
+            g_scored = [pb.scored(j) for j in range(len(crops))]
+            pb.close()
+            t0 = time.perf_counter()
+            cpu = Parallel(n_jobs=workers)(delayed(_cpu_score_whole)((G, ch, expected, MODEL, THRESHOLD, wl.res)) for G, ch in crops)
+            secs = time.perf_counter() - t0
+            pix = int(sum(len(c[1]) for c in cpu))
+            same_pixels, loops_equal, max_dp, flips, n_cmp, n_loops_cmp = True, True, 0.0, 0, 0, 0
+            for (gi, gj, gp), gl, (clist, probas, cl) in zip(g_scored, g_loops, cpu):
+                if len(gp) != len(probas) or not (np.array_equal(gi, clist[:, 0]) and np.array_equal(gj, clist[:, 1])):
+                    same_pixels = False
+                    continue
+                n_cmp += len(gp)
+                if len(gp):
+                    max_dp = max(max_dp, float(np.max(np.abs(gp - probas))))
+                    flips += int(np.count_nonzero((gp >= THRESHOLD) != (probas >= THRESHOLD)))
+                mine_l = sorted(zip(gl[0].tolist(), gl[1].tolist()))
+                loops_equal &= (mine_l == cl)
+                n_loops_cmp += len(cl)
             line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": workers, "kind": "port",
-                "sample": "%d work units = %d assemblies x candidate slices of %d (%d pixels), oracle/pyport.py "
-                          "(reference-faithful Python port) over joblib loky n_jobs=%d, %.1f s"
-                          % (workers, len(items), CPU_SLICE, pix, workers, secs)}
+                "value": pix / secs, "unit": UNIT, "cores": workers, "kind": "port",
+                "sample": "%d whole matrices of %d bins (diagonal crops around the first junction of %d assemblies of this "
+                          "workload, %d pixels), oracle/pyport.py (reference-faithful Python port: Peakachu init, candidates, "
+                          "getwindow, predict_proba, threshold, pooling) over joblib loky n_jobs=%d, %.1f s"
+                          % (len(crops), CROP, len(crops), pix, workers, secs)}
+            line["parity"] = {"loop_set_equal": bool(loops_equal and same_pixels), "scored_pixel_list_equal": bool(same_pixels),
+                              "max_abs_dp": max_dp, "flips": flips, "n_compared": n_cmp, "loops_compared": n_loops_cmp,
+                              "threshold": THRESHOLD,
+                              "against": "the cpu_baseline run above: same matrices, same forest, GPU through ScoreBatch / score_and_pool"}
         print(json.dumps(line))
     resident.close()
     if world > 1:

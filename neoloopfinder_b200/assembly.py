@@ -169,6 +169,13 @@ class complexSV(Fusion):
         self._fusion_matrix = None
         if map_only:
             return
+        self._build_matrix()
+
+    def _build_matrix(self):
+        """Second half of ``reorganize_matrix``: the contact data of the blocks laid out by the geometry
+        half (assembly.py:458-492).  Separate so that a caller can validate the geometry
+        (``len(Map) != n``: overlapping blocks) before any matrix is fetched or allocated."""
+        blocks, orients, index, n = self.blocks, self.orients, self.index, self._n_bins
         if hasattr(self.clr, "device_pixels") and n > 0:
             # SURVEY.md section 8 row f-2: the sample's pixel table is resident in HBM; the rearranged matrix
             # and the bias vector are built there (no region fetches, no host n x n matrix, no upload)

@@ -20,7 +20,6 @@ import logging
 import logging.handlers
 import os
 import sys
-import threading
 import traceback
 from typing import Dict, List, Optional
 
@@ -42,9 +41,87 @@ def _regress_chunk(tasks, expected):
     return [linear_regression_fit(le, expected, 5) for le in tasks]
 
 
+ASSEMBLY_BUDGET_MB = 16384      # device memory one sub-batch of assemblies may hold (NLF_ASSEMBLY_BUDGET_MB)
+MAX_JOBS_PER_BATCH = 4096       # below the library's NLF_MAX_JOBS (16384)
+
+
+def _assembly_bytes(n_bins):
+    """Device footprint of one assembly until its sub-batch is closed: the n x n fusion matrix, its band
+    (416 doubles per row) and the probability plane (13 * 32 doubles per row)."""
+    return 8 * n_bins * n_bins + 8 * n_bins * (416 + 416)
+
+
+def _score_chunk(clr, live, assemblies, rsize, balance, prob, mmp, nopool, forest, expected, ctx, stats, nproc, out,
+                 collect=None):
+    """Normalise, score and annotate one sub-batch of valid assemblies [(ID, complexSV)]."""
+    from .assembly import complexSV
+    from .scoring import ScoreBatch, score_and_pool
+    res = clr.binsize
+    batch = None
+    try:
+        for _ID, fu in live:
+            fu._build_matrix()
+        # normalisation: diagonal means on the GPU for every assembly, then all regressions, then rescale
+        task_lists = [fu.regression_tasks() for _ID, fu in live]
+        flat = [t for tl in task_lists for t in tl]
+        if nproc > 1 and len(flat) > 8:
+            from joblib import Parallel, delayed
+            chunk = max(1, len(flat) // (nproc * 4))
+            chunks = [flat[k:k + chunk] for k in range(0, len(flat), chunk)]
+            parts = Parallel(n_jobs=nproc)(delayed(_regress_chunk)(ch, expected) for ch in chunks)
+            fitted = [r for part in parts for r in part]
+        else:
+            fitted = _regress_chunk(flat, expected)
+        k = 0
+        for (_ID, fu), tl in zip(live, task_lists):
+            fu.apply_regressions(fitted[k:k + len(tl)])
+            k += len(tl)
+            fu.remove_gaps()
+        exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
+        batch = ScoreBatch(4, 400, ctx)               # upper = 400*res // res (scripts/neoloop-caller:202)
+        chains = []
+        for _ID, fu in live:
+            asm = fu._device_assembly()
+            batch.add_assembly(asm)
+            chain_of = np.array([fu.chains[k] for k in range(fu._n_bins)])
+            chains.append(chain_of[asm.kept_index()])     # chains[index_map[i]] per gap-free bin
+            if collect is not None:
+                collect[_ID] = (asm.gap_free(), chains[-1])
+        loops_by_job, (n_cand, n_scored, n_don) = score_and_pool(batch, forest, exp_arr, prob, res, mmp, chains, nopool)
+        if stats is not None:
+            stats["candidates"] = stats.get("candidates", 0) + int(n_cand.sum())
+            stats["scored"] = stats.get("scored", 0) + int(n_scored.sum())
+            stats["donuts"] = stats.get("donuts", 0) + int(n_don.sum())
+            stats["sub_batches"] = stats.get("sub_batches", 0) + 1
+
+        for job, (ID, fu) in enumerate(live):
+            li, lj, lp = loops_by_job[job]
+            loop_index = [(int(a), int(b), float(p)) for a, b, p in zip(li, lj, lp)]
+            loops = fu.index_to_coordinates(loop_index)
+            # keep calls inside the ORIGINAL (flexible) assembly only; geometry without re-fetching
+            fu2 = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu', expected_values=expected)
+            fu2.reorganize_matrix(map_only=True)
+            out[ID] = {k: (ID, v[0], v[1]) for k, v in loops.items()
+                       if (k[0], k[1]) in fu2.Map and (k[3], k[4]) in fu2.Map}
+    finally:
+        # the sub-batch's device memory goes back before the next one is built
+        for _ID, fu in live:
+            if fu._asm is not None:
+                fu._asm.close()
+                fu._asm = None
+        if batch is not None:
+            batch.close()
+
+
 def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model, expected, ctx=None,
-                    stats=None, nproc=1):
+                    stats=None, nproc=1, budget_mb=None, collect=None):
     """pipeline() for many assemblies on one GPU, batched.  Returns {ID: final_dict or None}.
+    ``collect`` (a dict) receives {ID: (gap-free matrix on the host, block id per gap-free bin)}.
+
+    Assemblies are validated from their geometry alone (an invalid one costs no device memory) and
+    processed in sub-batches bounded by a device-memory budget and by the library's job limit; every
+    sub-batch is closed before the next one is built, so an assembly file of any length runs in
+    bounded memory.  Results are per assembly: the split does not change them.
 
     The per-block-pair regressions (HuberRegressor, host-bound, ~5 ms each, ~18 per simple
     assembly) dominate the wall time once the scoring runs on the GPU; with nproc > 1 they are
@@ -52,65 +129,30 @@ def call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, mod
     from . import _lib
     from .assembly import complexSV
     from .forest import DeviceForest, load_forest
-    from .scoring import ScoreBatch, score_and_pool
 
     ctx = ctx or _lib.Context.get()
     forest = model if isinstance(model, DeviceForest) else load_forest(model, ctx)
-    res = clr.binsize
+    if budget_mb is None:
+        budget_mb = int(os.environ.get("NLF_ASSEMBLY_BUDGET_MB", ASSEMBLY_BUDGET_MB))
+    budget = max(1, int(budget_mb)) << 20
     out = {}
-    live = []
+    live, held = [], 0
     for ID in ids:
         fu = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu',
                        expected_values=expected, flexible=False)
         fu._ctx = ctx
-        fu.reorganize_matrix()
+        fu.reorganize_matrix(map_only=True)
         if len(fu.Map) != fu._n_bins:
             out[ID] = None                         # invalid assembly (scripts/neoloop-caller:196-197)
             continue
+        need = _assembly_bytes(fu._n_bins)
+        if live and (held + need > budget or len(live) >= MAX_JOBS_PER_BATCH):
+            _score_chunk(clr, live, assemblies, rsize, balance, prob, mmp, nopool, forest, expected, ctx, stats, nproc, out, collect)
+            live, held = [], 0
         live.append((ID, fu))
-    if not live:
-        return out
-    # normalisation: diagonal means on the GPU for every assembly, then all regressions, then rescale
-    task_lists = [fu.regression_tasks() for _ID, fu in live]
-    flat = [t for tl in task_lists for t in tl]
-    if nproc > 1 and len(flat) > 8:
-        from joblib import Parallel, delayed
-        chunk = max(1, len(flat) // (nproc * 4))
-        chunks = [flat[k:k + chunk] for k in range(0, len(flat), chunk)]
-        parts = Parallel(n_jobs=nproc)(delayed(_regress_chunk)(ch, expected) for ch in chunks)
-        fitted = [r for part in parts for r in part]
-    else:
-        fitted = _regress_chunk(flat, expected)
-    k = 0
-    for (_ID, fu), tl in zip(live, task_lists):
-        fu.apply_regressions(fitted[k:k + len(tl)])
-        k += len(tl)
-        fu.remove_gaps()
-    exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
-    batch = ScoreBatch(4, 400, ctx)               # upper = 400*res // res (scripts/neoloop-caller:202)
-    chains = []
-    for _ID, fu in live:
-        asm = fu._device_assembly()
-        batch.add_assembly(asm)
-        chain_of = np.array([fu.chains[k] for k in range(fu._n_bins)])
-        chains.append(chain_of[asm.kept_index()])     # chains[index_map[i]] per gap-free bin
-    loops_by_job, (n_cand, n_scored, n_don) = score_and_pool(batch, forest, exp_arr, prob, res, mmp, chains, nopool)
-    if stats is not None:
-        stats["candidates"] = stats.get("candidates", 0) + int(n_cand.sum())
-        stats["scored"] = stats.get("scored", 0) + int(n_scored.sum())
-        stats["donuts"] = stats.get("donuts", 0) + int(n_don.sum())
-
-    for job, (ID, fu) in enumerate(live):
-        li, lj, lp = loops_by_job[job]
-        loop_index = [(int(a), int(b), float(p)) for a, b, p in zip(li, lj, lp)]
-        loops = fu.index_to_coordinates(loop_index)
-        # keep calls inside the ORIGINAL (flexible) assembly only; geometry without re-fetching
-        fu2 = complexSV(clr, assemblies[ID], span=rsize, col=balance, protocol='insitu', expected_values=expected)
-        fu2.reorganize_matrix(map_only=True)
-        out[ID] = {k: (ID, v[0], v[1]) for k, v in loops.items()
-                   if (k[0], k[1]) in fu2.Map and (k[3], k[4]) in fu2.Map}
-        fu._device_assembly().close()
-    batch.close()
+        held += need
+    if live:
+        _score_chunk(clr, live, assemblies, rsize, balance, prob, mmp, nopool, forest, expected, ctx, stats, nproc, out, collect)
     return out
 
 
@@ -121,13 +163,33 @@ def pipeline(clr, index, assemblies, rsize, balance, prob, mmp, nopool, models_b
                            expected)[index]
 
 
-def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, nopool, model_path, expected,
-                    devices: Optional[List[int]] = None, stats=None, nproc=1):
-    """All assemblies of one resolution, sharded over GPUs by assembly (no collective: the
-    per-assembly results are KB-sized dictionaries merged on the host)."""
+def _device_worker(dev, clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, nproc, budget_mb):
+    """Body of one per-GPU worker process (or thread): its own CUDA context, forest copy and pixel table."""
     from . import _lib
+    ctx = _lib.Context.get(dev)
+    st = {}
+    r = call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, ctx, st, nproc,
+                        budget_mb)
+    st["launches"] = ctx.launch_count()
+    return r, st
+
+
+def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, nopool, model_path, expected,
+                    devices: Optional[List[int]] = None, stats=None, nproc=1, workers: Optional[str] = None,
+                    budget_mb=None):
+    """All assemblies of one resolution, sharded over GPUs by assembly (no collective: the
+    per-assembly results are KB-sized dictionaries merged on the host).
+
+    With more than one device every GPU is driven by its own worker PROCESS (spawned, so each has its
+    own interpreter and CUDA context: the Python-side geometry, dictionary building and regression
+    glue of different GPUs never share a GIL) -- the reference's own fan-out is one loky process per
+    assembly (scripts/neoloop-caller:155-159).  ``workers='thread'`` (or NLF_WORKERS=thread) keeps
+    everything in this process, one thread per GPU; it is also what a non-picklable model handle needs."""
+    from . import _lib
+    from .forest import DeviceForest
     if devices is None:
         devices = list(range(_lib.device_count()))
+    devices = list(dict.fromkeys(int(d) for d in devices))          # a context must not be driven by two workers
     if not devices:
         raise RuntimeError("no CUDA device visible: neoloopfinder_b200 has no CPU fallback")
     ids = list(assemblies)
@@ -135,32 +197,36 @@ def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, 
     # cost estimate from the assembly geometry only
     weights = [assembly_weight(assemblies[ID], rsize, res) for ID in ids]
     shards = lpt_shards(weights, len(devices))
+    jobs = [(d, [ids[k] for k in s]) for d, s in zip(devices, shards) if s]
+    per_dev_nproc = max(1, nproc // max(1, len(jobs)))
+    mode = workers or os.environ.get("NLF_WORKERS", "process")
+    if isinstance(model_path, DeviceForest):
+        mode = "thread"
     results: Dict[str, Optional[dict]] = {}
-    errors = []
+    per_dev = []
 
-    def work(dev, idx):
-        try:
-            ctx = _lib.Context.get(dev)
-            st = {} if stats is not None else None
-            r = call_assemblies(clr, [ids[k] for k in idx], assemblies, rsize, balance, prob, mmp, nopool,
-                                model_path, expected, ctx, st, max(1, nproc // len(devices)))
-            results.update(r)
-            if stats is not None:
-                for k, v in st.items():
-                    stats[k] = stats.get(k, 0) + v
-        except BaseException as exc:      # noqa: BLE001 - re-raised in the caller thread
-            errors.append(exc)
+    def run(dev, mine):
+        return _device_worker(dev, clr, mine, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected,
+                              per_dev_nproc, budget_mb)
 
-    if len(devices) == 1:
-        work(devices[0], shards[0])
+    if len(jobs) <= 1:
+        per_dev = [run(*j) for j in jobs]
+    elif mode == "thread":
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            per_dev = list(ex.map(lambda j: run(*j), jobs))
     else:
-        threads = [threading.Thread(target=work, args=(d, s)) for d, s in zip(devices, shards) if s]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-    if errors:
-        raise errors[0]
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(max_workers=len(jobs), mp_context=mp.get_context("spawn")) as ex:
+            futs = [ex.submit(_device_worker, d, clr, mine, assemblies, rsize, balance, prob, mmp, nopool, model_path,
+                              expected, per_dev_nproc, budget_mb) for d, mine in jobs]
+            per_dev = [f.result() for f in futs]
+    for r, st in per_dev:
+        results.update(r)
+        if stats is not None:
+            for k, v in st.items():
+                stats[k] = stats.get(k, 0) + v
     return [results[ID] for ID in ids]
 
 

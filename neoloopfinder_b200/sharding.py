@@ -54,7 +54,8 @@ def gather_dicts(local: Dict, group=None) -> Optional[Dict]:
     return out
 
 
-def call_resolution_distributed(clr, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, stats=None):
+def call_resolution_distributed(clr, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, stats=None,
+                                nproc=1, ctx=None):
     """One resolution under torchrun: every rank (one GPU each) calls its shard, results are
     gathered on all ranks in assembly order."""
     import torch.distributed as dist
@@ -63,6 +64,7 @@ def call_resolution_distributed(clr, assemblies, rsize, balance, prob, mmp, nopo
     world = dist.get_world_size() if dist.is_initialized() else 1
     ids = list(assemblies)
     mine = shard_ids(ids, assemblies, rsize, clr.binsize, world)[rank]
-    local = call_assemblies(clr, mine, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, stats=stats)
+    local = call_assemblies(clr, mine, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, ctx=ctx,
+                            stats=stats, nproc=nproc)
     merged = gather_dicts(local)
     return [merged[i] for i in ids]

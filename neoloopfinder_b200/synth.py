@@ -157,6 +157,62 @@ def make_workload(kind: str, res: int = 10000, seed: int = 0, n_assemblies: int 
     return clr, lines
 
 
+def assembly_blocks(clr, line: str, span: int):
+    """[(chrom, lo_bin, hi_bin)] of the blocks ``complexSV(..., flexible=False)`` builds for one assembly
+    line (neoloop/assembly.py:408-440), geometry only."""
+    from .assembly import complexSV
+    fu = complexSV(clr, line, span=span, col="sweight", expected_values={}, flexible=False)
+    fu.reorganize_matrix(map_only=True)
+    return [clr._bin_extent(tuple(r)) for r in fu.blocks]
+
+
+def _assembly_pixels(clr, line, span):
+    """Stored pixels (global bin1 <= bin2, count) of every block pair of one assembly."""
+    blocks = assembly_blocks(clr, line, span)
+    offs = {c: clr._chrom_offset(c) for c, _lo, _hi in blocks}
+    keys, vals = [], []
+    total = np.int64(sum(clr._nbins(c) for c in clr.chromnames))
+    for j1, (c1, lo1, hi1) in enumerate(blocks):
+        for (c2, lo2, hi2) in blocks[j1:]:
+            B = np.asarray(clr._raw_block(c1, lo1, hi1, c2, lo2, hi2))
+            rr, cc = np.nonzero(B)
+            gi = rr.astype(np.int64) + (lo1 + offs[c1])
+            gj = cc.astype(np.int64) + (lo2 + offs[c2])
+            keys.append(np.minimum(gi, gj) * total + np.maximum(gi, gj))
+            vals.append(B[rr, cc].astype(np.int32))
+    return (np.concatenate(keys), np.concatenate(vals)) if keys else (np.zeros(0, np.int64), np.zeros(0, np.int32))
+
+
+def regional_pixel_cooler(clr, lines: Dict[str, str], span: int, nproc: int = 1):
+    """A ``PixelCooler`` (cooler's pixel table, the format that lives in HBM) holding every pixel the
+    assemblies in ``lines`` read from ``clr``: all block pairs of every assembly.  The rest of the
+    genome stays empty, so an hg38-sized 5 kb table for ~200 assemblies is a few hundred MB instead of
+    the whole map; bins, chromosomes and weights are genome-wide as in a real ``.cool``.
+    ``complexSV.reorganize_matrix`` reads the same values from it as from ``clr`` itself."""
+    from .coolshim import PixelCooler
+    items = list(lines.values())
+    if nproc > 1 and len(items) > 1:
+        from joblib import Parallel, delayed
+        parts = Parallel(n_jobs=nproc)(delayed(_assembly_pixels)(clr, ln, span) for ln in items)
+    else:
+        parts = [_assembly_pixels(clr, ln, span) for ln in items]
+    names = list(clr.chromnames)
+    nb = [clr._nbins(c) for c in names]
+    total = int(sum(nb))
+    key = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.int64)
+    val = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int32)
+    key, first = np.unique(key, return_index=True)              # sorted by (bin1, bin2); regions may overlap
+    val = val[first]
+    bin1 = key // total
+    bin2 = (key - bin1 * total).astype(np.int32)
+    indptr = np.zeros(total + 1, dtype=np.int64)
+    np.cumsum(np.bincount(bin1, minlength=total), out=indptr[1:])
+    weights = {col: np.concatenate([clr._weights(c, 0, n, col) for c, n in zip(names, nb)])
+               for col in ("weight", "sweight")}
+    sizes = {c: int(clr._chromsizes[c]) for c in names}
+    return PixelCooler(clr.binsize, sizes, indptr, bin2, val, weights)
+
+
 def analytic_expected(clr: SyntheticCooler, maxdis: int = 5_000_000) -> Dict[int, float]:
     """Closed-form stand-in for ``calculate_expected`` on a SyntheticCooler.
 

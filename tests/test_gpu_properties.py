@@ -18,12 +18,12 @@ def workload():
     import bench
     from neoloopfinder_b200 import _lib
     from neoloopfinder_b200.forest import load_forest
-    bench.select_workload("cfg2", N_ASM)
+    wl = bench.Workload("cfg2", N_ASM)
     ctx = _lib.Context.get(0)
-    clr, lines, expected = bench.build_assemblies(0, N_ASM)
-    mats, chains = bench.gap_free_matrices_gpu(clr, lines, expected, ctx)
-    exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
+    clr, lines, expected = wl.build()
     forest = load_forest(os.path.join(GOLDEN, "forest_w6.joblib"), ctx)
+    mats, chains = bench.gap_free_matrices(clr, list(lines), lines, expected, ctx, forest, wl.res)
+    exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
     assert len(mats) >= 8 and min(m.shape[0] for m in mats) > 500
     return ctx, mats, chains, exp_arr, forest
 

@@ -9,7 +9,8 @@ from neoloopfinder_b200.forest import load_forest
 
 ctx = _lib.Context.get(0)
 forest = load_forest(bench.MODEL, ctx)
-clr, lines, expected = bench.build_assemblies(0, 16)
+WL = bench.Workload(os.environ.get("NLF_TOOL_WORKLOAD", "cfg2"), 16)
+clr, lines, expected = WL.build()
 ids = list(lines)
 call_assemblies(clr, ids[:2], lines, bench.SPAN, "sweight", 0.9, 2, False, forest, expected, ctx)   # warm-up
 t0 = time.perf_counter()

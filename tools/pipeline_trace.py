@@ -11,9 +11,10 @@ from neoloopfinder_b200.scoring import ScoreBatch, score_and_pool, score_matrice
 
 ctx = _lib.Context.get(0)
 forest = load_forest(bench.MODEL, ctx)
-clr, lines, expected = bench.build_assemblies(0, 50)
+WL = bench.Workload(os.environ.get("NLF_TOOL_WORKLOAD", "cfg2"), 50)
+clr, lines, expected = WL.build()
 exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
-mats, chains = bench.gap_free_matrices_gpu(clr, lines, expected, ctx)
+mats, chains = bench.gap_free_matrices(clr, list(lines), lines, expected, ctx, forest, WL.res)
 pinned = [torch.from_numpy(G).pin_memory() for G in mats]
 host = [t.numpy() for t in pinned]
 for depth, first in ((1, 1.0), (2, 1.0), (4, 1.0), (4, 0.5), (4, 0.3), (5, 0.5), (5, 0.3), (6, 0.4)):

@@ -9,9 +9,10 @@ from neoloopfinder_b200.scoring import ScoreBatch
 
 ctx = _lib.Context.get(0)
 forest = load_forest(bench.MODEL, ctx)
-clr, lines, expected = bench.build_assemblies(0, 50)
+WL = bench.Workload(os.environ.get("NLF_TOOL_WORKLOAD", "cfg2"), 50)
+clr, lines, expected = WL.build()
 exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
-mats, chains = bench.gap_free_matrices_gpu(clr, lines, expected, ctx)
+mats, chains = bench.gap_free_matrices(clr, list(lines), lines, expected, ctx, forest, WL.res)
 b = ScoreBatch(4, 400, ctx)
 for G in mats:
     b.add_dense(G)
