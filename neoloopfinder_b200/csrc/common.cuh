@@ -4,6 +4,7 @@
 #include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a tool (ncu --nvtx, nsys) is attached
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -35,7 +36,8 @@ inline int fail(int code, const char *fmt, ...)
                              cudaGetErrorString(e__));                                              \
     } while (0)
 
-enum ProfClass { P_BANDIFY = 0, P_DIAG = 1, P_FEATURE = 2, P_FOREST = 3, P_THRESH = 4, P_NORM = 5, P_POOL = 6, P_NCLASS = 8 };
+enum ProfClass { P_BANDIFY = 0, P_DIAG = 1, P_FEATURE = 2, P_FOREST = 3, P_THRESH = 4, P_NORM = 5, P_POOL = 6, P_SCORE = 7, P_NCLASS = 9 };
+// P_SCORE: the whole feature + forest region of one nlf_batch_score call (the two kernels run concurrently on two streams)
 
 // numpy pairwise sum of ld(0..len-1) computed by an aligned group of 8 lanes (lane j = accumulator j
 // of every leaf); every lane of the group returns the sum.  numpy splits n > 128 at n/2 - (n/2)%8, so
@@ -167,6 +169,31 @@ struct nlf_ctx {
     // main stream.  The batch records an event after its last input; the main stream waits for it
     // before the first kernel that reads the bands.
     cudaStream_t copy_stream = nullptr;
+    // forest traversal runs here (highest priority), concurrently with the feature kernel of the next chunk on `stream`
+    cudaStream_t aux_stream = nullptr;
+    static constexpr int NEVT = 4;
+    cudaEvent_t ev_feat[NEVT] = {nullptr}, ev_forest[NEVT] = {nullptr};   // per feature-buffer set (re-recorded every use)
+    cudaError_t aux_init()
+    {
+        if (aux_stream) return cudaSuccess;
+        int lo = 0, hi = 0;
+        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+        for (int i = 0; i < NEVT; i++) {
+            if ((e = cudaEventCreateWithFlags(&ev_feat[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&ev_forest[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    void aux_release()
+    {
+        if (!aux_stream) return;
+        cudaStreamSynchronize(aux_stream);
+        for (int i = 0; i < NEVT; i++) { cudaEventDestroy(ev_feat[i]); cudaEventDestroy(ev_forest[i]); }
+        cudaStreamDestroy(aux_stream);
+        aux_stream = nullptr;
+    }
     cudaEvent_t fence = nullptr;
     struct Stage { void *p = nullptr; size_t bytes = 0; cudaEvent_t used = nullptr; bool pending = false; };
     static constexpr int NSTAGE = 3;
@@ -246,10 +273,16 @@ struct nlf_ctx {
     }
     void prof_resolve()
     {
+        static const bool trace = getenv("NLF_TRACE") != nullptr;     // per-launch timeline on stderr (tuning)
         for (auto &r : recs) {
             float ms = 0;
             cudaEventSynchronize(r.b);
             cudaEventElapsedTime(&ms, r.a, r.b);
+            if (trace && !recs.empty()) {
+                float t0 = 0;
+                cudaEventElapsedTime(&t0, recs.front().a, r.a);
+                fprintf(stderr, "nlf-trace class %d start %.3f ms dur %.3f ms\n", r.cls, t0, ms);
+            }
             prof_ms[r.cls] += ms;
             prof_n[r.cls] += 1;
             free_events.push_back(r.a);
@@ -283,7 +316,7 @@ struct KLaunch {
     static const char *range_name(int cls)
     {
         static const char *const names[nlf::P_NCLASS] = {"nlf:bandify", "nlf:diag_means+isotonic", "nlf:features", "nlf:forest",
-                                                         "nlf:threshold", "nlf:normalise", "nlf:pool", "nlf:other"};
+                                                         "nlf:threshold", "nlf:normalise", "nlf:pool", "nlf:score", "nlf:other"};
         return names[(cls >= 0 && cls < nlf::P_NCLASS) ? cls : nlf::P_NCLASS - 1];
     }
     KLaunch(nlf_ctx *ctx, int cls_, cudaStream_t st = nullptr) : c(ctx), cls(cls_), s(st ? st : ctx->stream)

@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <utility>
 
 #include "common.cuh"
 
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(FeatCfg<W, TXP>::NT, 2)
 k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, int njobs, int tile_offset,
            int lower, int upper, int pitch, int ndp, int ndt, const double *__restrict__ expv, int nexp, PixRef *__restrict__ pix,
            float *__restrict__ featT, unsigned *__restrict__ slot_counter, unsigned max_slots,
-           int *__restrict__ overflow, unsigned *__restrict__ nanmask)
+           int *__restrict__ overflow, unsigned *__restrict__ nanmask, unsigned slot_base)
 {
     using C = FeatCfg<W, TXP>;
     constexpr int S = C::S, F = C::F, TX = C::TX, TR = C::TR, TC = C::TC, VC = C::VC, NT = C::NT;
@@ -558,7 +560,7 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
             if (f_nan) atomicOr(&nanmask[my_slot >> 5], 1u << (my_slot & 31u));
             if (warp == 0) {
                 pix[my_slot] = make_uint2((unsigned)job, ((unsigned)x << 16) | (unsigned)(d0 + lane));
-                if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)my_slot;
+                if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)(slot_base + my_slot);
             }
         }
     }
@@ -969,6 +971,174 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
 #undef SM_F64
 }
 
+// =============================================================================================
+// K8, single pass over a COMPACT forest (the production kernel when the forest fits).
+// Only internal nodes are stored (8 bytes: float threshold + packed word); a leaf is a pointer, never a node:
+//   * a node with one leaf child keeps its internal child as the IMPLICIT next node (the node that follows
+//     it in memory) and points at the leaf explicitly; bit S says that the implicit child is the right one;
+//   * a node with two leaf children is TERMINAL: it carries both leaf references;
+//   * leaf references index a table of the forest's DISTINCT leaf values (class fractions repeat a lot),
+//     stored right behind the nodes, so "explicit child" is one address space.
+// For the bundled-shape forest (100 trees, 32 048 sklearn nodes) that is 15 974 nodes + 307 values = 127 KB
+// instead of 256 KB: the whole forest sits in the shared memory of ONE CTA, next to a CTA of the feature
+// kernel on the same SM -- one forest pass per pixel, no partial sums through HBM, and the fp64 pipe
+// (features of the next chunk) and the LSU (traversal of this chunk) work at the same time.
+// Global word y: bit 31 CONT (non-terminal), bit 30 S (CONT) / 1 (terminal), bits 29-22 feature,
+// bits 21-0: CONT: explicit child slot (node index, or n_int + leaf reference); terminal: left reference |
+// right reference << 11.  Staged in shared memory (CONT nodes): 1<<31 | (address of the explicit child >> 3)
+// << 16 | feature << 5 | S, as in k_forest_pipe.  Work decomposition, TMA tile pipeline, tree-ordered fp64
+// summation: as k_forest_pipe; the traversal stores 16-bit leaf references, the summing warp looks them up.
+// =============================================================================================
+struct Forest3Dev {
+    const uint2 *nodes;       // [n_int]
+    const double *leafv;      // [n_leaf] distinct class-1 fractions, all in [0, 2)
+    const unsigned *root;     // [n_trees] slot of the root (node index, or n_int + leaf reference for a one-leaf tree)
+    int n_int, n_leaf, n_trees;
+};
+
+static inline size_t forest3_smem(int F, int T, int n_int, int n_leaf)
+{
+    return 2 * (size_t)F * 128 + 2 * (size_t)T * 64 + 256 + 8 * (size_t)n_int + 8 * (size_t)n_leaf +
+           4 * (size_t)((T + 8 + 3) & ~3) + 16;
+}
+
+template <int NW, int ILP>
+__global__ void __launch_bounds__(32 * NW, 1)
+k_forest_one(Forest3Dev fr, int F, const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask,
+             const float *__restrict__ featT, const unsigned *__restrict__ slot_counter, const JobDev *__restrict__ jobs,
+             int lower, int W, int ndp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[2], done[2];
+    const int T = fr.n_trees;
+    const unsigned tile_bytes = (unsigned)F * 128u;
+    const unsigned lid_bytes = (unsigned)T * 64u;
+    const unsigned o_lid = 2 * tile_bytes;
+    const unsigned o_cnt = o_lid + 2 * lid_bytes;
+    const unsigned o_nodes = o_cnt + 256u;
+    const unsigned o_leaf = o_nodes + 8u * (unsigned)fr.n_int;
+    const unsigned o_root = o_leaf + 8u * (unsigned)fr.n_leaf;
+#define SM_U2(off) (*reinterpret_cast<uint2 *>(smem_raw + (off)))
+#define SM_U32(off) (*reinterpret_cast<unsigned *>(smem_raw + (off)))
+#define SM_U16(off) (*reinterpret_cast<unsigned short *>(smem_raw + (off)))
+#define SM_F64(off) (*reinterpret_cast<double *>(smem_raw + (off)))
+    const unsigned sbase = smem_u32(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < fr.n_int; k += blockDim.x) {
+        uint2 nd = fr.nodes[k];
+        if ((int)nd.y < 0)
+            nd.y = 0x80000000u | (((sbase + o_nodes + ((nd.y & 0x3fffffu) << 3)) >> 3) << 16) | (((nd.y >> 22) & 0xffu) << 5) |
+                   ((nd.y >> 30) & 1u);
+        SM_U2(o_nodes + 8u * k) = nd;
+    }
+    for (int k = tid; k < fr.n_leaf; k += blockDim.x) SM_F64(o_leaf + 8u * k) = fr.leafv[k];
+    // root table; entries [T, T + 8) point at leaf slot 0 (a chain that starts there ends at once)
+    for (int k = tid; k < T + 8; k += blockDim.x)
+        SM_U32(o_root + 4u * k) = 0x40000u + sbase + o_nodes + 8u * (k < T ? fr.root[k] : (unsigned)fr.n_int);
+    if (tid < 64) SM_U32(o_cnt + 4u * tid) = 0u;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&done[0], 32 * NW);
+        mbar_init(&done[1], 32 * NW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned leaf_biased = 0x40000u + sbase + o_leaf;
+    const unsigned nslots = *slot_counter;
+    const unsigned ngroups = (nslots + 31u) >> 5;
+    const int dlo = max(lower, W + 2);
+    const unsigned stride = gridDim.x;
+    unsigned g = blockIdx.x;
+    if (tid == 0) {
+        if (g < ngroups) {
+            mbar_expect_tx(&full[0], tile_bytes);
+            tma_load_1d(smem_raw, featT + (size_t)g * F * 32, tile_bytes, &full[0]);
+        }
+        if (g + stride < ngroups) {
+            mbar_expect_tx(&full[1], tile_bytes);
+            tma_load_1d(smem_raw + tile_bytes, featT + (size_t)(g + stride) * F * 32, tile_bytes, &full[1]);
+        }
+    }
+    unsigned nanm = (g < ngroups) ? nanmask[g] : 0u;
+    for (unsigned it = 0; g < ngroups; it++, g += stride) {
+        const unsigned buf = it & 1u;
+        const unsigned par = (it >> 1) & 1u;
+        const unsigned gn = g + stride;
+        const unsigned nanm_n = (gn < ngroups) ? nanmask[gn] : 0u;
+        mbar_wait(&full[buf], par);
+        const bool active = (g * 32u + lane < nslots) && !((nanm >> lane) & 1u);
+        if (active) {
+            const unsigned my = sbase + buf * tile_bytes + (unsigned)lane * 4u;
+            const unsigned lid = o_lid + buf * lid_bytes + (unsigned)lane * 2u;
+            unsigned *cnt = reinterpret_cast<unsigned *>(smem_raw + o_cnt + buf * 128u + (unsigned)lane * 4u);
+            int t = (int)atomicAdd(cnt, (unsigned)ILP);
+            while (t < T) {
+                unsigned na[ILP];
+                uint2 nd[ILP];
+#pragma unroll
+                for (int c = 0; c < ILP; c++) na[c] = SM_U32(o_root + 4u * (unsigned)(t + c));
+#pragma unroll
+                for (int c = 0; c < ILP; c++) nd[c] = lds_node(na[c]);
+                while (true) {
+                    unsigned any = nd[0].y;
+#pragma unroll
+                    for (int c = 1; c < ILP; c++) any |= nd[c].y;
+                    if ((int)any >= 0) break;
+#pragma unroll
+                    for (int c = 0; c < ILP; c++) {
+                        if ((int)nd[c].y < 0) {
+                            const float xv = lds_f32(scaled_add4(nd[c].y & 0x1fe0u, my));
+                            const bool imp = (xv <= __uint_as_float(nd[c].x)) != (bool)(nd[c].y & 1u);
+                            na[c] = imp ? na[c] + 8u : (nd[c].y >> 13);
+                            nd[c] = lds_node(na[c]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < ILP; c++) {
+                    unsigned ref;
+                    if (nd[c].y & 0x40000000u) {
+                        // terminal node: one more comparison picks one of its two leaves
+                        const float xv = lds_f32(my + ((nd[c].y >> 15) & 0x7f80u));
+                        ref = (xv <= __uint_as_float(nd[c].x)) ? (nd[c].y & 0x7ffu) : ((nd[c].y >> 11) & 0x7ffu);
+                    } else {
+                        ref = (na[c] - leaf_biased) >> 3;       // the address IS the leaf
+                    }
+                    if (t + c < T) SM_U16(lid + 64u * (unsigned)(t + c)) = (unsigned short)ref;
+                }
+                t = (int)atomicAdd(cnt, (unsigned)ILP);
+            }
+        }
+        mbar_arrive(&done[buf]);                      // release: this thread's leaf references are published
+        if (warp == (int)(it % NW)) {
+            mbar_wait(&done[buf], par);               // acquire: every thread is through with this tile
+            if (active) {
+                const unsigned lid = o_lid + buf * lid_bytes + (unsigned)lane * 2u;
+                double acc = 0.0;
+                for (int tt = 0; tt < T; tt++)
+                    acc = __dadd_rn(acc, SM_F64(o_leaf + 8u * (unsigned)SM_U16(lid + 64u * (unsigned)tt)));
+                const PixRef px = pix[g * 32u + lane];
+                const JobDev J = jobs[px.x];
+                J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T);
+            }
+            SM_U32(o_cnt + buf * 128u + (unsigned)lane * 4u) = 0u;
+            __syncwarp();
+            const unsigned g2 = g + 2 * stride;
+            if (lane == 0 && g2 < ngroups) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads/writes before the async-proxy write
+                mbar_expect_tx(&full[buf], tile_bytes);
+                tma_load_1d(smem_raw + (size_t)buf * tile_bytes, featT + (size_t)g2 * F * 32, tile_bytes, &full[buf]);
+            }
+        }
+        nanm = nanm_n;
+    }
+#undef SM_U2
+#undef SM_U32
+#undef SM_U16
+#undef SM_F64
+}
+
 // pixels with NaN features: general traversal from global memory with missing_go_to_left routing
 __global__ void k_forest_nan(ForestDev fr, const PixRef *__restrict__ pix, const unsigned *__restrict__ nanmask,
                              const float *__restrict__ featT, const unsigned *__restrict__ slot_counter,
@@ -1261,6 +1431,12 @@ struct nlf_forest {
     int *d_off = nullptr;
     long long n_nodes = 0;
     std::vector<int> off;            // host copy of tree offsets
+    // compact single-pass format (k_forest_one), NULL when the forest cannot be expressed in it
+    uint2 *d_nodes3 = nullptr;
+    double *d_leafv3 = nullptr;
+    unsigned *d_root3 = nullptr;
+    int n_int3 = 0, n_leaf3 = 0;
+    double visits_per_tree = 0;      // mean root-to-leaf comparisons (unweighted over leaves; informative)
 };
 
 constexpr int NLF_MAX_JOBS = 16384;     // jobs per batch (status / counter pool size)
@@ -1359,6 +1535,7 @@ NLF_EXPORT int nlf_ctx_destroy(nlf_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->stream);
+    c->aux_release();
     c->prof_resolve();
     c->big_release_all();
     c->stage_release_all();
@@ -1375,6 +1552,7 @@ NLF_EXPORT int nlf_ctx_sync(nlf_ctx *c)
 {
     NLF_CUDA(cudaSetDevice(c->device));
     NLF_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (c->aux_stream) NLF_CUDA(cudaStreamSynchronize(c->aux_stream));
     NLF_CUDA(cudaStreamSynchronize(c->stream));
     return NLF_OK;
 }
@@ -1474,6 +1652,88 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
             nodes2[(size_t)(b + k)] = nd;
         }
     }
+    // compact format: internal nodes only, depth-first with the IMPLICIT child right behind its parent
+    // (see k_forest_one).  Usable when thresholds and leaf values are non-negative and below 2 (the staged
+    // words keep their two top bits for flags), there are at most 2048 distinct leaf values (11-bit
+    // references in terminal nodes) and every index fits its field.
+    std::vector<uint2> nodes3;
+    std::vector<double> leafv3;
+    std::vector<unsigned> root3((size_t)n_trees);
+    bool v3_ok = true;
+    {
+        std::map<uint64_t, unsigned> leaf_ref;
+        auto ref_of = [&](long long node) -> unsigned {
+            const double v = leaf_p1[node];
+            uint64_t bits;
+            memcpy(&bits, &v, 8);
+            auto it = leaf_ref.find(bits);
+            if (it != leaf_ref.end()) return it->second;
+            const unsigned r = (unsigned)leafv3.size();
+            leaf_ref[bits] = r;
+            leafv3.push_back(v);
+            return r;
+        };
+        long long n_internal = 0;
+        for (long long k = 0; k < total; k++) {
+            if (left[k] >= 0) {
+                n_internal++;
+                if (!(threshold[k] >= 0.0 && threshold[k] < 2.0)) v3_ok = false;
+            } else if (!(leaf_p1[k] >= 0.0 && leaf_p1[k] < 2.0) || std::signbit(leaf_p1[k])) {
+                v3_ok = false;
+            }
+        }
+        if (n_internal >= (1 << 21)) v3_ok = false;
+        const unsigned LEAF = 0x80000000u;                 // marks "slot = n_internal + reference" until n_internal is final
+        struct Item { long long node; long long patch; };  // patch: compact index of the parent whose explicit field waits
+        std::vector<std::pair<unsigned, unsigned>> leaf_fix;   // (compact node, leaf reference) of explicit leaf children
+        for (int t = 0; t < n_trees && v3_ok; t++) {
+            const long long b = tree_off[t];
+            if (left[b] < 0) { root3[(size_t)t] = LEAF | ref_of(b); continue; }
+            root3[(size_t)t] = (unsigned)nodes3.size();
+            std::vector<Item> stack;
+            stack.push_back({b, -1});
+            while (!stack.empty()) {
+                const Item itx = stack.back();
+                stack.pop_back();
+                const long long k = itx.node;
+                const unsigned idx = (unsigned)nodes3.size();
+                if (itx.patch >= 0) nodes3[(size_t)itx.patch].y |= idx;
+                const long long L = b + left[k], R = b + right[k];
+                const bool lleaf = left[L] < 0, rleaf = left[R] < 0;
+                uint2 nd;
+                nd.x = nodes[(size_t)k].x;                                  // largest float <= threshold
+                nd.y = ((unsigned)feature[k] & 0xffu) << 22;
+                if (lleaf && rleaf) {
+                    const unsigned rl = ref_of(L), rr = ref_of(R);
+                    if (rl >= 2048u || rr >= 2048u) { v3_ok = false; break; }
+                    nd.y |= 0x40000000u | rl | (rr << 11);                 // terminal
+                    nodes3.push_back(nd);
+                } else if (!lleaf && !rleaf) {
+                    nd.y |= 0x80000000u;                                     // implicit left, explicit right (patched later)
+                    nodes3.push_back(nd);
+                    stack.push_back({R, (long long)idx});
+                    stack.push_back({L, -1});                                // popped next: lands at idx + 1
+                } else if (rleaf) {
+                    nd.y |= 0x80000000u;                                     // implicit left, explicit right leaf
+                    nodes3.push_back(nd);
+                    leaf_fix.push_back({idx, ref_of(R)});
+                    stack.push_back({L, -1});
+                } else {
+                    nd.y |= 0x80000000u | 0x40000000u;                       // S: the implicit child is the right one
+                    nodes3.push_back(nd);
+                    leaf_fix.push_back({idx, ref_of(L)});
+                    stack.push_back({R, -1});
+                }
+            }
+        }
+        // explicit leaf children and one-leaf trees: slot = number of internal nodes + reference
+        const unsigned n_int = (unsigned)nodes3.size();
+        if (n_int + leafv3.size() >= (1u << 22) || leafv3.empty()) v3_ok = false;
+        if (v3_ok) {
+            for (auto &fx : leaf_fix) nodes3[fx.first].y |= n_int + fx.second;
+            for (auto &r : root3) if (r & LEAF) r = n_int + (r & ~LEAF);
+        }
+    }
     NLF_CUDA(cudaSetDevice(ctx->device));
     nlf_forest *f = new nlf_forest();
     f->ctx = ctx;
@@ -1494,6 +1754,17 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
     f->dev.tree_off = f->d_off;
     f->dev.n_trees = n_trees;
     f->dev.n_features = n_features;
+    if (v3_ok) {
+        f->n_int3 = (int)nodes3.size();
+        f->n_leaf3 = (int)leafv3.size();
+        NLF_CUDA(cudaMalloc(&f->d_nodes3, sizeof(uint2) * std::max<size_t>(1, nodes3.size())));
+        NLF_CUDA(cudaMalloc(&f->d_leafv3, sizeof(double) * leafv3.size()));
+        NLF_CUDA(cudaMalloc(&f->d_root3, sizeof(unsigned) * (size_t)n_trees));
+        if (!nodes3.empty())
+            NLF_CUDA(cudaMemcpy(f->d_nodes3, nodes3.data(), sizeof(uint2) * nodes3.size(), cudaMemcpyHostToDevice));
+        NLF_CUDA(cudaMemcpy(f->d_leafv3, leafv3.data(), sizeof(double) * leafv3.size(), cudaMemcpyHostToDevice));
+        NLF_CUDA(cudaMemcpy(f->d_root3, root3.data(), sizeof(unsigned) * (size_t)n_trees, cudaMemcpyHostToDevice));
+    }
     *out = f;
     return NLF_OK;
 }
@@ -1504,6 +1775,9 @@ NLF_EXPORT int nlf_forest_destroy(nlf_forest *f)
     cudaSetDevice(f->ctx->device);
     cudaFree(f->d_nodes);
     if (f->d_nodes2) cudaFree(f->d_nodes2);
+    if (f->d_nodes3) cudaFree(f->d_nodes3);
+    if (f->d_leafv3) cudaFree(f->d_leafv3);
+    if (f->d_root3) cudaFree(f->d_root3);
     cudaFree(f->d_leaf);
     cudaFree(f->d_off);
     delete f;
@@ -1695,34 +1969,66 @@ static int feat_tx(int w)
     int tx = (w >= 7) ? 16 : 32;
     if (const char *e = getenv("NLF_FEAT_TX")) {
         const int v = atoi(e);
-        if ((w >= 7 && (v == 8 || v == 16)) || (w < 7 && (v == 16 || v == 32))) tx = v;
+        if ((w >= 7 && (v == 8 || v == 16)) || (w < 7 && (v == 12 || v == 14 || v == 16 || v == 32))) tx = v;
     }
     return tx;
 }
 
+// where one chunk of tiles puts its scored pixels: a region of the batch's feature buffers
+struct ChunkBuf {
+    PixRef *pix;
+    float *featT;
+    unsigned *nanmask;
+    unsigned *counter;
+    unsigned max_slots;
+    unsigned slot_base;      // first slot of the region inside the batch's buffers (for the kept-slot accessors)
+};
+
 template <int W, int TXP>
-static int launch_features_tx(nlf_batch *b, int tile_offset, int n_tiles, int nexp)
+static const void *feature_kernel() { return reinterpret_cast<const void *>(&k_features<W, TXP>); }
+
+static const void *feature_kernel_ptr(int w, int tx)
 {
-    using C = FeatCfg<W, TXP>;
-    nlf_ctx *c = b->ctx;
-    const size_t dyn = sizeof(double) * 2 * C::TR * C::TC;
-    static bool configured[64] = {false};
-    if (!configured[c->device & 63]) {
-        NLF_CUDA(cudaFuncSetAttribute(k_features<W, TXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        configured[c->device & 63] = true;
-    }
-    KLaunch k(c, P_FEATURE);
-    k_features<W, TXP><<<n_tiles, C::NT, dyn, c->stream>>>(
-        b->d_jobs, b->d_tile_base, (int)b->jobs.size(), tile_offset, b->lower, b->upper, b->pitch, b->ndp, b->ndt,
-        b->d_exp, nexp, b->d_pix, b->d_featT, b->d_group_counter, b->max_groups * 32u, b->d_overflow, b->d_nanmask);
-    return NLF_OK;
+    if (w == 5)
+        return tx == 32 ? feature_kernel<5, 32>() : tx == 16 ? feature_kernel<5, 16>() : tx == 14 ? feature_kernel<5, 14>()
+                                                                                                : feature_kernel<5, 12>();
+    if (w == 6)
+        return tx == 32 ? feature_kernel<6, 32>() : tx == 16 ? feature_kernel<6, 16>() : tx == 14 ? feature_kernel<6, 14>()
+                                                                                                : feature_kernel<6, 12>();
+    return tx == 16 ? feature_kernel<7, 16>() : feature_kernel<7, 8>();
 }
 
-static int launch_features(nlf_batch *b, int w, int tx, int tile_offset, int n_tiles, int nexp)
+static size_t feature_dyn_smem(int w, int tx) { return sizeof(double) * 2 * (size_t)(tx + 2 * w) * (32 + 4 * w); }
+
+static int launch_features(nlf_batch *b, int w, int tx, int tile_offset, int n_tiles, int nexp, const ChunkBuf &cb)
 {
-    if (w == 5) return tx == 32 ? launch_features_tx<5, 32>(b, tile_offset, n_tiles, nexp) : launch_features_tx<5, 16>(b, tile_offset, n_tiles, nexp);
-    if (w == 6) return tx == 32 ? launch_features_tx<6, 32>(b, tile_offset, n_tiles, nexp) : launch_features_tx<6, 16>(b, tile_offset, n_tiles, nexp);
-    return tx == 16 ? launch_features_tx<7, 16>(b, tile_offset, n_tiles, nexp) : launch_features_tx<7, 8>(b, tile_offset, n_tiles, nexp);
+    nlf_ctx *c = b->ctx;
+    const void *kern = feature_kernel_ptr(w, tx);
+    const size_t dyn = feature_dyn_smem(w, tx);
+    static bool configured[64][3][5] = {{{false}}};
+    const int ti = tx == 32 ? 0 : tx == 16 ? 1 : tx == 14 ? 2 : tx == 12 ? 3 : 4;
+    if (!configured[c->device & 63][w - 5][ti]) {
+        NLF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        // same shared-memory carve-out as the forest kernel, so that CTAs of both can share an SM
+        NLF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[c->device & 63][w - 5][ti] = true;
+    }
+    const JobDev *jobs = b->d_jobs;
+    const int *tile_base = b->d_tile_base;
+    int njobs = (int)b->jobs.size();
+    const double *expv = b->d_exp;
+    PixRef *pix = cb.pix;
+    float *featT = cb.featT;
+    unsigned *counter = cb.counter;
+    unsigned max_slots = cb.max_slots;
+    int *overflow = b->d_overflow;
+    unsigned *nanmask = cb.nanmask;
+    unsigned slot_base = cb.slot_base;
+    void *args[] = {&jobs, &tile_base, &njobs, &tile_offset, &b->lower, &b->upper, &b->pitch, &b->ndp, &b->ndt, &expv, &nexp,
+                    &pix, &featT, &counter, &max_slots, &overflow, &nanmask, &slot_base};
+    KLaunch k(c, P_FEATURE);
+    NLF_CUDA(cudaLaunchKernel(kern, dim3((unsigned)n_tiles), dim3(32u * (2 * w + 1)), args, dyn, c->stream));
+    return NLF_OK;
 }
 
 // dynamic shared memory of the cooperative forest kernels for a part of `nodes` nodes in `ntree` trees
@@ -1732,8 +2038,116 @@ static inline size_t forest_dyn_smem(size_t nodes, int ntree, int F)
            sizeof(int) * (size_t)((ntree + 8 + 3) & ~3) + 64;
 }
 
-// K8 launch: shared-memory forest parts when they fit, else the global-memory kernel.
-static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
+// How one nlf_batch_score call runs the feature and the forest kernels.
+struct ScorePlan {
+    bool one = false;        // single-pass compact forest (k_forest_one)
+    bool coop = false;       // ... launched on the aux stream, sharing every SM with the feature kernel of the next chunk
+    int tx = 32;             // matrix rows per feature tile
+    int nw = 32;             // warps of the forest CTA
+    size_t forest_smem = 0;
+};
+
+template <int NW>
+static const void *forest_one_kernel() { return reinterpret_cast<const void *>(&k_forest_one<NW, 2>); }
+
+static const void *forest_one_ptr(int nw)
+{
+    return nw == 32 ? forest_one_kernel<32>() : nw == 24 ? forest_one_kernel<24>() : nw == 20 ? forest_one_kernel<20>()
+                                                                                            : forest_one_kernel<16>();
+}
+
+// Decide the plan from the real resource numbers of the compiled kernels: the forest CTA (whole compact forest
+// + two feature tiles + leaf references) and ONE feature CTA must fit an SM together (shared memory incl. the
+// 1 KB the system reserves per CTA, registers per warp in units of 512); the tile height shrinks until they do.
+static int make_plan(nlf_batch *b, nlf_forest *f, int w, int F, ScorePlan *out)
+{
+    ScorePlan p;
+    p.tx = feat_tx(w);
+    const size_t smem_block_max = 232448;                      // 227 KB opt-in limit per block on sm_100
+    const size_t smem_sm = 233472;                             // 228 KB per SM
+    // NLF_SCORE_MODE = parts | one | coop.  Measured on the bench forest (profiles/r02_score_modes.md): the two-part
+    // kernel (k_forest_pipe) is the fastest, the single-pass compact kernel pays ~2 extra instructions per node step
+    // for its swap bit (+15 %), and sharing the SMs with the feature kernel is limited by the register file of
+    // an SM sub-partition (4 feature warps x 72 registers leave room for 20 forest warps, which traverse 34 %
+    // slower than 32).  Default: parts while the forest needs at most two of them, else the single pass.
+    const char *mode = getenv("NLF_SCORE_MODE");
+    const bool small_forest = f->d_nodes2 && (size_t)f->n_nodes * 8 <= 2 * (size_t)150 * 1024;
+    const bool allow_one = mode ? strcmp(mode, "parts") != 0 : !small_forest;
+    const bool allow_coop = mode && !strcmp(mode, "coop");
+    if (f->d_nodes3 && allow_one) {
+        p.forest_smem = forest3_smem(F, f->dev.n_trees, f->n_int3, f->n_leaf3);
+        cudaFuncAttributes fa;
+        NLF_CUDA(cudaFuncGetAttributes(&fa, forest_one_ptr(32)));
+        p.one = p.forest_smem + fa.sharedSizeBytes <= smem_block_max;
+        if (p.one && allow_coop && !b->keep_slots) {
+            const int cands5[] = {32, 16, 14, 12}, cands7[] = {16, 8};
+            const int *cands = w >= 7 ? cands7 : cands5;
+            const int ncand = w >= 7 ? 2 : 4;
+            const char *etx = getenv("NLF_FEAT_TX");
+            for (int k = 0; k < ncand && !p.coop; k++) {
+                const int tx = cands[k];
+                if (etx && tx != p.tx) continue;               // the knob pins the height
+                cudaFuncAttributes ka;
+                NLF_CUDA(cudaFuncGetAttributes(&ka, feature_kernel_ptr(w, tx)));
+                const size_t feat_smem = ka.sharedSizeBytes + feature_dyn_smem(w, tx) + 1024;
+                if (feat_smem + p.forest_smem + fa.sharedSizeBytes + 1024 > smem_sm) continue;
+                const int feat_regs = ((ka.numRegs * 32 + 511) / 512) * 512 * (2 * w + 1);
+                const int nws[] = {32, 24, 20, 16};
+                for (int q = 0; q < 4; q++) {
+                    cudaFuncAttributes qa;
+                    NLF_CUDA(cudaFuncGetAttributes(&qa, forest_one_ptr(nws[q])));
+                    if (feat_regs + ((qa.numRegs * 32 + 511) / 512) * 512 * nws[q] <= 65536) {
+                        p.coop = true;
+                        p.tx = tx;
+                        p.nw = nws[q];
+                        break;
+                    }
+                }
+            }
+        }
+        if (const char *e = getenv("NLF_FOREST_NW")) {
+            const int v = atoi(e);
+            if (v == 32 || v == 24 || v == 20 || v == 16) p.nw = v;
+        }
+    }
+    *out = p;
+    return NLF_OK;
+}
+
+static int launch_forest_one(nlf_batch *b, nlf_forest *f, int w, int F, const ScorePlan &p, const ChunkBuf &cb, cudaStream_t st)
+{
+    nlf_ctx *c = b->ctx;
+    const void *kern = forest_one_ptr(p.nw);
+    static bool configured[64][4] = {{false}};
+    const int qi = p.nw == 32 ? 0 : p.nw == 24 ? 1 : p.nw == 20 ? 2 : 3;
+    if (!configured[c->device & 63][qi]) {
+        NLF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 64));
+        NLF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[c->device & 63][qi] = true;
+    }
+    Forest3Dev fd{f->d_nodes3, f->d_leafv3, f->d_root3, f->n_int3, f->n_leaf3, f->dev.n_trees};
+    const PixRef *pix = cb.pix;
+    const unsigned *nanmask = cb.nanmask;
+    const float *featT = cb.featT;
+    const unsigned *counter = cb.counter;
+    const JobDev *jobs = b->d_jobs;
+    void *args[] = {&fd, &F, &pix, &nanmask, &featT, &counter, &jobs, &b->lower, &w, &b->ndp};
+    {
+        KLaunch k(c, P_FOREST, st);
+        NLF_CUDA(cudaLaunchKernel(kern, dim3((unsigned)c->sm_count), dim3(32u * p.nw), args, p.forest_smem, st));
+    }
+    {
+        // pixels with NaN features (rare: constant windows) through the general kernel
+        KLaunch k(c, P_FOREST, st);
+        k_forest_nan<<<c->sm_count * 4, 256, 0, st>>>(f->dev, cb.pix, cb.nanmask, cb.featT, cb.counter, b->d_jobs, b->lower, w, b->ndp);
+        NLF_CUDA(cudaGetLastError());
+    }
+    return NLF_OK;
+}
+
+// K8 launch (fallback when the compact forest is unusable): shared-memory forest parts when they fit, else the
+// global-memory kernel.
+static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F, const ChunkBuf &cb)
 {
     nlf_ctx *c = b->ctx;
     const size_t smem_max = 232448;                            // 227 KB opt-in limit per block on sm_100
@@ -1775,7 +2189,7 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
         size_t smem = sizeof(float) * (size_t)GW * F * 32;
         NLF_CUDA(cudaFuncSetAttribute(k_forest<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KLaunch k(c, P_FOREST);
-        k_forest<GW><<<c->sm_count * 2, 32 * GW, smem, c->stream>>>(f->dev, b->d_pix, b->d_featT, b->d_group_counter,
+        k_forest<GW><<<c->sm_count * 2, 32 * GW, smem, c->stream>>>(f->dev, cb.pix, cb.featT, cb.counter,
                                                                     b->d_jobs, b->lower, w, b->ndp);
         NLF_CUDA(cudaGetLastError());
         return NLF_OK;
@@ -1797,7 +2211,7 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
     }
     const int nparts = (int)part_begin.size() - 1;
     double *acc = nullptr;
-    if (nparts > 1) NLF_CUDA(cudaMallocAsync(&acc, sizeof(double) * (size_t)b->max_groups * 32, c->stream));
+    if (nparts > 1) NLF_CUDA(cudaMallocAsync(&acc, sizeof(double) * (size_t)cb.max_slots, c->stream));
     for (int p = 0; p < nparts; p++) {
         int t0 = part_begin[p], t1 = part_begin[p + 1];
         size_t smem = forest_dyn_smem((size_t)(f->off[t1] - f->off[t0]), t1 - t0, F);
@@ -1808,7 +2222,7 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
             NLF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                        \
                                           (int)(smem_max - 64)));                                                   \
             kern<<<c->sm_count, 32 * A, smem, c->stream>>>(                                                         \
-                f->d_nodes2, f->d_off, t0, t1, T, F, b->d_pix, b->d_nanmask, b->d_featT, b->d_group_counter,        \
+                f->d_nodes2, f->d_off, t0, t1, T, F, cb.pix, cb.nanmask, cb.featT, cb.counter,                      \
                 b->d_jobs, b->lower, w, b->ndp, acc, p == 0, p == nparts - 1);                                      \
         } while (0)
         switch (cfg) {
@@ -1827,8 +2241,8 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
     {
         // pixels with NaN features (rare: constant windows) through the general kernel
         KLaunch k(c, P_FOREST);
-        k_forest_nan<<<c->sm_count * 4, 256, 0, c->stream>>>(f->dev, b->d_pix, b->d_nanmask, b->d_featT,
-                                                             b->d_group_counter, b->d_jobs, b->lower, w, b->ndp);
+        k_forest_nan<<<c->sm_count * 4, 256, 0, c->stream>>>(f->dev, cb.pix, cb.nanmask, cb.featT,
+                                                             cb.counter, b->d_jobs, b->lower, w, b->ndp);
         NLF_CUDA(cudaGetLastError());
     }
     if (acc) NLF_CUDA(cudaFreeAsync(acc, c->stream));
@@ -1836,11 +2250,11 @@ static int launch_forest(nlf_batch *b, nlf_forest *f, int w, int F)
 }
 
 // upload the per-job descriptors (pointers into the batch pools; NULL pools stay NULL)
-static int upload_jobs(nlf_batch *b, int w)
+static int upload_jobs(nlf_batch *b, int w, int tx = 0)
 {
     nlf_ctx *c = b->ctx;
     const int nj = (int)b->jobs.size();
-    const int TX = b->TX = feat_tx(w);               // FeatCfg<W, TX>::TX
+    const int TX = b->TX = (tx > 0 ? tx : feat_tx(w));   // FeatCfg<W, TX>::TX
     const int up1 = b->upper + 2;
     std::vector<JobDev> jd(nj);
     std::vector<int> tb(nj + 1);
@@ -1958,39 +2372,87 @@ NLF_EXPORT int nlf_batch_score(nlf_batch *b, nlf_forest *f, const double *expect
     NLF_CUDA(cudaMallocAsync(&b->d_don_j, sizeof(int) * b->don_cap, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_don_p, sizeof(double) * b->don_cap, c->stream));
     NLF_CUDA(cudaMallocAsync(&b->d_don_v, sizeof(double) * b->don_cap, c->stream));
-    rc = upload_jobs(b, w);
+    ScorePlan plan;
+    rc = make_plan(b, f, w, F, &plan);
     if (rc) return rc;
-    // Feature memory is bounded: tiles are processed in chunks whose worst-case feature footprint
-    // (TX*32 slots of F floats per tile) stays below the budget, each chunk going through the feature
-    // and the forest kernels before the next one starts (results land in `prob` by pixel coordinates).
+    rc = upload_jobs(b, w, plan.tx);
+    if (rc) return rc;
+    // Tiles are processed in chunks: every chunk goes through the feature kernel and then the forest kernel
+    // (results land in `prob` by pixel coordinates).  With the compact forest the two kernels of DIFFERENT
+    // chunks run at the same time: features of chunk k+1 on the main stream, traversal of chunk k on the aux
+    // stream, CTAs of both on every SM (fp64 pipe and LSU are different units).  The chunks rotate through
+    // NBUF feature buffers whose total worst-case footprint (TX*32 slots of F floats per tile) stays below
+    // the budget; a buffer is reused once the forest kernel that read it has finished.
     const int tiles = b->total_tiles;
     const int TXh = b->TX;
     size_t budget_mb = 12288;
     if (const char *e = getenv("NLF_FEATURE_BUDGET_MB")) budget_mb = (size_t)std::max(1, atoi(e));
     const size_t slot_bytes = (size_t)F * 4 + sizeof(PixRef) + 8;
-    long long tiles_per_chunk = (long long)((budget_mb << 20) / (slot_bytes * TXh * 32));
+    const size_t tile_bytes = slot_bytes * TXh * 32;
+    int nbuf = plan.coop ? 3 : 1;
+    long long tiles_per_chunk = (long long)((budget_mb << 20) / (tile_bytes * nbuf));
+    if (plan.coop) {
+        long long target = std::max<long long>((tiles + 7) / 8, 4LL * c->sm_count);
+        if (const char *e = getenv("NLF_CHUNK_TILES")) target = std::max(1, atoi(e));
+        tiles_per_chunk = std::min(tiles_per_chunk, target);
+    }
     tiles_per_chunk = std::max(1LL, std::min<long long>(tiles_per_chunk, tiles));
     const int n_chunks = (int)((tiles + tiles_per_chunk - 1) / tiles_per_chunk);
     if (n_chunks > 1 && b->keep_slots)
         return fail(NLF_ERR_ARG, "batch needs %d feature chunks: features cannot be kept (raise NLF_FEATURE_BUDGET_MB or split the batch)", n_chunks);
+    nbuf = std::min(nbuf, n_chunks);
     const long long groups = tiles_per_chunk * TXh;            // 32 slots per group, TX*32 slots per tile
     b->max_groups = (unsigned)groups;
-    NLF_CUDA(c->big_alloc((void **)&b->d_pix, sizeof(PixRef) * (size_t)groups * 32));
-    NLF_CUDA(c->big_alloc((void **)&b->d_featT, sizeof(float) * (size_t)groups * F * 32));
-    NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned), c->stream));
-    NLF_CUDA(c->big_alloc((void **)&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1)));
+    NLF_CUDA(c->big_alloc((void **)&b->d_pix, sizeof(PixRef) * (size_t)groups * 32 * nbuf));
+    NLF_CUDA(c->big_alloc((void **)&b->d_featT, sizeof(float) * (size_t)groups * F * 32 * nbuf));
+    NLF_CUDA(cudaMallocAsync(&b->d_group_counter, sizeof(unsigned) * n_chunks, c->stream));
+    NLF_CUDA(c->big_alloc((void **)&b->d_nanmask, sizeof(unsigned) * (size_t)(groups + 1) * nbuf));
     NLF_CUDA(cudaMallocAsync(&b->d_overflow, sizeof(int), c->stream));
     NLF_CUDA(cudaMemsetAsync(b->d_overflow, 0, sizeof(int), c->stream));
+    NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned) * n_chunks, c->stream));
+    const bool two_streams = plan.coop && n_chunks > 1;
+    if (two_streams) NLF_CUDA(c->aux_init());
+    cudaEvent_t region_a = nullptr;
+    if (c->profile) {
+        region_a = c->get_event();
+        NLF_CUDA(cudaEventRecord(region_a, c->stream));
+    }
     for (int ch = 0; ch < n_chunks; ch++) {
         const int t_off = (int)(ch * tiles_per_chunk);
         const int t_cnt = (int)std::min<long long>(tiles_per_chunk, tiles - t_off);
-        NLF_CUDA(cudaMemsetAsync(b->d_group_counter, 0, sizeof(unsigned), c->stream));
-        NLF_CUDA(cudaMemsetAsync(b->d_nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
-        rc = launch_features(b, w, TXh, t_off, t_cnt, nexp);
+        const int set = ch % nbuf;
+        ChunkBuf cb;
+        cb.pix = b->d_pix + (size_t)set * groups * 32;
+        cb.featT = b->d_featT + (size_t)set * groups * F * 32;
+        cb.nanmask = b->d_nanmask + (size_t)set * (groups + 1);
+        cb.counter = b->d_group_counter + ch;
+        cb.max_slots = (unsigned)(groups * 32);
+        cb.slot_base = (unsigned)((size_t)set * groups * 32);
+        if (two_streams && ch >= nbuf) NLF_CUDA(cudaStreamWaitEvent(c->stream, c->ev_forest[set], 0));   // buffer `set` is free again
+        NLF_CUDA(cudaMemsetAsync(cb.nanmask, 0, sizeof(unsigned) * (size_t)(groups + 1), c->stream));
+        rc = launch_features(b, w, TXh, t_off, t_cnt, nexp, cb);
         if (rc) return rc;
         NLF_CUDA(cudaGetLastError());
-        rc = launch_forest(b, f, w, F);
-        if (rc) return rc;
+        if (two_streams) {
+            NLF_CUDA(cudaEventRecord(c->ev_feat[set], c->stream));
+            NLF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_feat[set], 0));
+            rc = launch_forest_one(b, f, w, F, plan, cb, c->aux_stream);
+            if (rc) return rc;
+            NLF_CUDA(cudaEventRecord(c->ev_forest[set], c->aux_stream));
+        } else if (plan.one) {
+            rc = launch_forest_one(b, f, w, F, plan, cb, c->stream);
+            if (rc) return rc;
+        } else {
+            rc = launch_forest(b, f, w, F, cb);
+            if (rc) return rc;
+        }
+    }
+    if (two_streams)                                           // the aux stream is in order: its last event covers every chunk
+        NLF_CUDA(cudaStreamWaitEvent(c->stream, c->ev_forest[(n_chunks - 1) % nbuf], 0));
+    if (region_a) {
+        cudaEvent_t region_b = c->get_event();
+        NLF_CUDA(cudaEventRecord(region_b, c->stream));
+        c->recs.push_back({P_SCORE, region_a, region_b});
     }
     {
         KLaunch k(c, P_THRESH);
