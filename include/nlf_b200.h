@@ -198,6 +198,9 @@ int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const int *yi, lon
 int nlf_distance_normalize(nlf_ctx *ctx, const double *windows, long long N, const int *xi, const int *yi,
                            int w, const double *expected, int nexp, double *out, uint8_t *pass);
 /* Drop the results but keep the matrices resident, so nlf_batch_score can run again. */
+/* Apply another probability threshold to a scored batch (callers.py:623-628 again): the Donut list and the
+ * per-job scored / Donut counts are rebuilt from the probabilities kept in HBM; nothing is re-scored. */
+int nlf_batch_rethreshold(nlf_batch *b, double thre);
 int nlf_batch_reset(nlf_batch *b);
 int nlf_batch_njobs(nlf_batch *b);
 int nlf_batch_destroy(nlf_batch *b);
@@ -226,6 +229,11 @@ int nlf_pool_peak_heights(nlf_ctx *ctx, int n_buckets, const int64_t *bucket_off
  * nlf_pool_peak_heights), NULL = stable order. */
 int nlf_pool_find_anchors(nlf_ctx *ctx, const int *pos, int npos, int res, int min_count, int min_dis_bp,
                           const int *order, int *anchors_out, int cap, int *n_anchors);
+/* Same with the caller's peak-width window `wlen_bp` (Peakachu.find_anchors(..., wlen=...), callers.py:740-749:
+ * wlen = min(wlen_bp // res, 20) bins at res <= 10 kb, 4 bins above; a window of one bin or less is scipy's
+ * "`wlen` must be larger than 1" error). */
+int nlf_pool_find_anchors_wlen(nlf_ctx *ctx, const int *pos, int npos, int res, int min_count, int min_dis_bp,
+                               int wlen_bp, const int *order, int *anchors_out, int cap, int *n_anchors);
 /* Peakachu._cluster_core (callers.py:786-831) on points already sorted by descending
  * (value, (i, j)): is_final_out[k] = 1 when point k is appended to final_list, pooled_out[k] = 1
  * when it joins `visited`.  r_bins is the method's r (bins). */

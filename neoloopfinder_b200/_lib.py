@@ -84,6 +84,8 @@ _SIGNATURES = {
     "nlf_batch_destroy": (C.c_int, [vp]),
     "nlf_pool": (C.c_int, [vp, C.c_int, i64p, ip, ip, dp, C.c_int, C.c_int, C.c_int, ip, i64p, ip, i64p, u8p]),
     "nlf_pool_find_anchors": (C.c_int, [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, ip]),
+    "nlf_pool_find_anchors_wlen": (C.c_int, [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, ip]),
+    "nlf_batch_rethreshold": (C.c_int, [vp, C.c_double]),
     "nlf_pool_cluster_core": (C.c_int, [vp, ip, ip, C.c_int, C.c_int, u8p, u8p]),
     "nlf_pool_peak_heights": (C.c_int, [vp, C.c_int, i64p, ip, C.c_int, C.c_int, C.c_int, dp, i64p, ip]),
 }
@@ -150,10 +152,26 @@ class Context:
         check(load().nlf_ctx_create(int(device), C.byref(self.h)))
         self.device = int(device)
 
+    @staticmethod
+    def default_device() -> int:
+        """NLF_DEVICE, else LOCAL_RANK (torchrun), else -- inside a pool worker such as the loky processes the
+        reference fans assemblies out to (scripts/neoloop-caller:155-159) -- worker number modulo the visible
+        GPUs, else 0 (device = worker_id mod n_gpus)."""
+        for key in ("NLF_DEVICE", "LOCAL_RANK"):
+            if key in os.environ:
+                return int(os.environ[key])
+        import multiprocessing
+        import re
+        m = re.search(r"(\d+)$", multiprocessing.current_process().name)     # LokyProcess-3, SpawnPoolWorker-2, ...
+        if m is None:
+            return 0
+        n = device_count()
+        return (int(m.group(1)) - 1) % n if n > 1 else 0
+
     @classmethod
     def get(cls, device=None):
         if device is None:
-            device = int(os.environ.get("NLF_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            device = cls.default_device()
         key = (os.getpid(), device)
         if key not in cls._per_device:
             cls._per_device[key] = Context(device)

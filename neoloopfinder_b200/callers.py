@@ -347,14 +347,33 @@ class Fusion(object):
         return self._hcm
 
     def load_expected(self):
-        """Bundled GM12878 in-situ expected tables (neoloop/callers.py:120-134)."""
+        """Bundled GM12878 in-situ expected tables (neoloop/callers.py:120-134): {distance in bins: mean contact}
+        for 5, 10, 20, 25, 40 and 50 kb; any other resolution gets the reference's empty table.  The six pickles
+        are the reference's own data files and are not duplicated here: they are looked up in NLF_EXPECTED_DIR,
+        in this package's ``data/`` folder and in an installed ``neoloop`` package.  A missing table for a
+        supported resolution is an error -- with an empty table every regression would silently return (0, 0, False)
+        and every SV / assembly would be rejected."""
         import joblib
-        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
         name = {5000: "5k", 10000: "10k", 20000: "20k", 25000: "25k", 40000: "40k", 50000: "50k"}.get(self.res)
         self.expected = {}
-        path = os.path.join(here, f"gm.insitu.expected.{name}.pkl") if name else None
-        if path and os.path.exists(path):
-            self.expected = joblib.load(path)
+        if name is None:
+            return
+        fname = f"gm.insitu.expected.{name}.pkl"
+        folders = [os.environ.get("NLF_EXPECTED_DIR"), os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")]
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("neoloop")
+            if spec is not None and spec.submodule_search_locations:
+                folders.append(os.path.join(list(spec.submodule_search_locations)[0], "data"))
+        except (ImportError, ValueError):
+            pass
+        for folder in folders:
+            if folder and os.path.exists(os.path.join(folder, fname)):
+                self.expected = joblib.load(os.path.join(folder, fname))
+                return
+        raise FileNotFoundError(
+            f"{fname} not found (searched NLF_EXPECTED_DIR, {folders[1]} and an installed neoloop package): pass "
+            "expected_values=calculate_expected(clr, ...) or point NLF_EXPECTED_DIR at the reference's neoloop/data")
 
     def linear_regression(self, exp1, exp2, min_samples=5):
         """Slope of local vs global expected with a Huber fit (neoloop/callers.py:370-412)."""
@@ -530,13 +549,8 @@ class Peakachu():
             self._batch.score(self._forest, self.exp_arr, thre, self.w)
             self._scored_thre = thre
         elif self._scored_thre != thre:
-            # one batch is scored once; a different threshold needs a fresh pass
-            old = self._batch
-            self._batch = ScoreBatch(4, self._upper, self._ctx)
-            asm = getattr(self._matrix, "_nlf_assembly", None)
-            self._job = self._batch.add_assembly(asm) if asm is not None else self._batch.add_dense(np.asarray(self._matrix))
-            old.close()
-            self._batch.score(self._forest, self.exp_arr, thre, self.w)
+            # the probabilities stay in HBM: only the threshold pass (callers.py:623-628) runs again
+            self._batch.rethreshold(thre)
             self._scored_thre = thre
 
     def predict(self, thre, no_pool=False, min_count=2, index_map=None, chains=None):
@@ -559,6 +573,14 @@ class Peakachu():
         i, j, p = self._batch.scored(self._job)
         return np.stack([i, j], 1).astype(np.int64), p
 
+    def _context(self):
+        """The CUDA context of this object; a subclass that never ran ``Peakachu.__init__`` and only set ``self.r``
+        (``class Triangle(Peakachu)``, neoloop/visualize/core.py:23, :271, :315) gets the process default."""
+        ctx = self.__dict__.get("_ctx")
+        if ctx is None:
+            ctx = self._ctx = _lib.Context.get()
+        return ctx
+
     def local_clustering(self, Donuts, min_count=2, r=15000, index_map=None, chains=None):
         """Pool thresholded pixels per (chain, chain) region (callers.py:668-697)."""
         if not len(Donuts):
@@ -575,7 +597,7 @@ class Peakachu():
                 ys = np.array([index_map[j] for j in ij[:, 1]])
             ci = np.array([chains[x] for x in xs])
             cj = np.array([chains[y] for y in ys])
-        return local_clustering_gpu(ij, val, self.r, min_count, r, ci, cj, self._ctx)
+        return local_clustering_gpu(ij, val, self.r, min_count, r, ci, cj, self._context())
 
     def _local_clustering(self, Donuts, min_count=1, r=15000):
         """One region (callers.py:699-738) -> list of kept (i, j)."""
@@ -583,7 +605,7 @@ class Peakachu():
             return []
         ij = np.array(list(Donuts), dtype=np.int64).reshape(-1, 2)
         val = np.array([Donuts[(i, j)] for i, j in ij], dtype=np.float64)
-        mask = pool_buckets([(ij[:, 0], ij[:, 1], val)], self.r, min_count, r, self._ctx)[0]
+        mask = pool_buckets([(ij[:, 0], ij[:, 1], val)], self.r, min_count, r, self._context())[0]
         return [(int(a), int(b)) for a, b in ij[mask]]
 
     def find_anchors(self, pos, min_count=3, min_dis=15000, wlen=40000):
@@ -592,8 +614,8 @@ class Peakachu():
         GPU (the routine the pooling kernel uses); below 10 kb ties between equal peak heights follow
         numpy.argsort, exactly like the pooling path."""
         import ctypes as C
-        if wlen != 40000:
-            raise NotImplementedError("find_anchors: only the reference's window length (40000 bp) is built in")
+        if self.r <= 10000 and min(wlen // self.r, 20) <= 1:
+            raise ValueError("`wlen` must be larger than 1, was %d" % min(wlen // self.r, 20))      # scipy.signal.peak_widths
         pos = np.ascontiguousarray(list(pos), dtype=np.int32)
         if pos.size == 0:
             raise ValueError("min() arg is an empty sequence")              # Counter of nothing, as in the reference
@@ -604,7 +626,7 @@ class Peakachu():
             prio = np.empty(pos.size, dtype=np.float64)
             poff = np.zeros(2, dtype=np.int64)
             amb = C.c_int(0)
-            _lib.check(L.nlf_pool_peak_heights(self._ctx.h, 1, _lib.ptr(off, C.c_int64), _lib.ptr(pos, C.c_int), int(self.r),
+            _lib.check(L.nlf_pool_peak_heights(self._context().h, 1, _lib.ptr(off, C.c_int64), _lib.ptr(pos, C.c_int), int(self.r),
                                                int(min_count), int(min_dis), _lib.ptr(prio, C.c_double),
                                                _lib.ptr(poff, C.c_int64), C.byref(amb)))
             if amb.value:
@@ -613,9 +635,9 @@ class Peakachu():
         cap = int(pos.max() - pos.min()) + 1
         out = np.empty(3 * cap, dtype=np.int32)
         n = C.c_int(0)
-        _lib.check(L.nlf_pool_find_anchors(self._ctx.h, _lib.ptr(pos, C.c_int), int(pos.size), int(self.r), int(min_count),
-                                           int(min_dis), None if order is None else _lib.ptr(order, C.c_int),
-                                           _lib.ptr(out, C.c_int), cap, C.byref(n)))
+        _lib.check(L.nlf_pool_find_anchors_wlen(self._context().h, _lib.ptr(pos, C.c_int), int(pos.size), int(self.r), int(min_count),
+                                                int(min_dis), int(wlen), None if order is None else _lib.ptr(order, C.c_int),
+                                                _lib.ptr(out, C.c_int), cap, C.byref(n)))
         return {(int(a), int(b), int(c)) for a, b, c in out[:3 * n.value].reshape(-1, 3)}
 
     def _cluster_core(self, sort_list, r, visited, final_list):
@@ -630,7 +652,7 @@ class Peakachu():
         pi, pj = np.ascontiguousarray(ij[:, 0]), np.ascontiguousarray(ij[:, 1])
         fin = np.zeros(m, dtype=np.uint8)
         pooled = np.zeros(m, dtype=np.uint8)
-        _lib.check(_lib.load().nlf_pool_cluster_core(self._ctx.h, _lib.ptr(pi, C.c_int), _lib.ptr(pj, C.c_int), m, int(r),
+        _lib.check(_lib.load().nlf_pool_cluster_core(self._context().h, _lib.ptr(pi, C.c_int), _lib.ptr(pj, C.c_int), m, int(r),
                                                      _lib.ptr(fin, C.c_ubyte), _lib.ptr(pooled, C.c_ubyte)))
         for k in np.flatnonzero(fin):
             final_list.append((int(pi[k]), int(pj[k])))

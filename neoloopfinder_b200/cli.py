@@ -313,6 +313,11 @@ def getargs(argv=None):
                         help='''Model pickle(s), one per -H matrix in the same order; overrides the cache lookup.''')
     parser.add_argument('--gpus', default=None,
                         help='''Comma-separated CUDA device indices (default: every visible device).''')
+    parser.add_argument('--genome-wide', action='store_true',
+                        help='''Also call loops on every chromosome outside any SV assembly (each chromosome is scored as
+                        a trivial, junction-free assembly). --assembly becomes optional.''')
+    parser.add_argument('--chroms', nargs='+', default=None,
+                        help='''Chromosomes of the genome-wide call (default: all except unplaced contigs, chrM and EBV).''')
     commands = list(sys.argv[1:] if argv is None else argv)
     if not commands:
         commands.append('-h')
@@ -373,11 +378,14 @@ def run(argv=None):
 
         logger.info('Load assembled SVs')
         lines = {}
-        with open(args.assembly, 'r') as source:
-            for line in source:
-                parse = line.rstrip().split()
-                if parse:
-                    lines[parse[0]] = '\t'.join(parse[1:])
+        if args.assembly is None and not args.genome_wide:
+            raise ValueError('--assembly is required unless --genome-wide is given')
+        if args.assembly is not None:
+            with open(args.assembly, 'r') as source:
+                for line in source:
+                    parse = line.rstrip().split()
+                    if parse:
+                        lines[parse[0]] = '\t'.join(parse[1:])
 
         byres = {}
         for res in sorted(clrs, reverse=True):
@@ -388,12 +396,24 @@ def run(argv=None):
                                           nproc=args.nproc)
             logger.info('Done')
             stats = {}
-            results = call_resolution(clr, lines, args.region_size, balance, args.prob, args.min_marginal_peaks,
-                                      args.no_clustering, models_by_res[res], expected, devices, stats, args.nproc)
+            results = []
+            if lines:
+                results = call_resolution(clr, lines, args.region_size, balance, args.prob, args.min_marginal_peaks,
+                                          args.no_clustering, models_by_res[res], expected, devices, stats, args.nproc)
             logger.info('Scored {0} pixels ({1} candidates, {2} above the threshold)'.format(
                 stats.get('scored', 0), stats.get('candidates', 0), stats.get('donuts', 0)))
             logger.info('Merge loops across assemblies ...')
             byres[res] = merge_results(results)
+            if args.genome_wide:
+                from .genome import call_genome, genome_lines
+                names = args.chroms or [c for c in clr.chromnames if not any(t in c for t in ('_', 'M', 'EBV'))]
+                logger.info('Genome-wide call on {0} chromosomes ...'.format(len(names)))
+                gstats = {}
+                calls = call_genome(clr, models_by_res[res], expected, args.prob, args.min_marginal_peaks,
+                                    args.no_clustering, names, balance, devices, gstats)
+                logger.info('Scored {0} pixels on {1} bins'.format(gstats.get('scored', 0), gstats.get('bins', 0)))
+                for key, labels in genome_lines(calls, res).items():
+                    byres[res].setdefault(key, []).extend(labels)
 
         if len(clrs) > 1:
             logger.info('Combine loops from multiple resolutions')

@@ -98,11 +98,12 @@ __device__ void d_peak_width_bounds(const double *x, int n, int peak, int wlen_i
 // query != 0: only emit the height-filtered peak priorities (prio_out, *n_prio) and report in
 // *ambiguous whether two equal heights sit closer than the distance filter.
 __device__ int d_find_anchors(const int *pos, int npos, int res, int min_count, int r_bp, BucketWs &ws, Anchor *out,
-                              const int *ext_order, int query, double *prio_out, int *n_prio, int *ambiguous)
+                              const int *ext_order, int query, double *prio_out, int *n_prio, int *ambiguous,
+                              int wlen_bp = 40000)
 {
     int min_dis = r_bp / res; if (min_dis < 2) min_dis = 2;
     int wlen;
-    if (res <= 10000) { wlen = 40000 / res; if (wlen > 20) wlen = 20; } else wlen = 4;
+    if (res <= 10000) { wlen = wlen_bp / res; if (wlen > 20) wlen = 20; } else wlen = 4;
     int lo = pos[0], hi = pos[0];
     for (int i = 1; i < npos; i++) { lo = min(lo, pos[i]); hi = max(hi, pos[i]); }
     int n = hi - lo + 1;
@@ -716,12 +717,12 @@ NLF_EXPORT int nlf_pool_peak_heights(nlf_ctx *ctx, int n_buckets, const int64_t 
 // The two helper methods of Peakachu as callable entry points (the pooling kernel uses the same
 // device routines): find_anchors (callers.py:740-784) and _cluster_core (callers.py:786-831).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_find_anchors_one(const int *pos, int npos, int res, int min_count, int r_bp, const int *order,
+__global__ void k_find_anchors_one(const int *pos, int npos, int res, int min_count, int r_bp, int wlen_bp, const int *order,
                                    char *ws_base, int range, int *out, int *n_out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     BucketWs ws = carve(ws_base, range, npos);
-    const int k = d_find_anchors(pos, npos, res, min_count, r_bp, ws, ws.xa, order, 0, nullptr, nullptr, nullptr);
+    const int k = d_find_anchors(pos, npos, res, min_count, r_bp, ws, ws.xa, order, 0, nullptr, nullptr, nullptr, wlen_bp);
     for (int q = 0; q < k; q++) { out[3 * q] = ws.xa[q].summit; out[3 * q + 1] = ws.xa[q].lb; out[3 * q + 2] = ws.xa[q].rb; }
     *n_out = k;
 }
@@ -740,7 +741,15 @@ __global__ void __launch_bounds__(256) k_cluster_core_one(const int *pi, const i
 NLF_EXPORT int nlf_pool_find_anchors(nlf_ctx *ctx, const int *pos, int npos, int res, int min_count, int min_dis_bp,
                                      const int *order, int *anchors_out, int cap, int *n_anchors)
 {
+    return nlf_pool_find_anchors_wlen(ctx, pos, npos, res, min_count, min_dis_bp, 40000, order, anchors_out, cap, n_anchors);
+}
+
+NLF_EXPORT int nlf_pool_find_anchors_wlen(nlf_ctx *ctx, const int *pos, int npos, int res, int min_count, int min_dis_bp,
+                                          int wlen_bp, const int *order, int *anchors_out, int cap, int *n_anchors)
+{
     if (!ctx || !pos || npos <= 0 || res <= 0 || !anchors_out || !n_anchors) return fail(NLF_ERR_ARG, "nlf_pool_find_anchors: bad arguments");
+    if (res <= 10000 && std::min(wlen_bp / res, 20) <= 1)
+        return fail(NLF_ERR_ARG, "`wlen` must be larger than 1, was %d", std::min(wlen_bp / res, 20));
     int lo = pos[0], hi = pos[0];
     for (int i = 1; i < npos; i++) { lo = std::min(lo, pos[i]); hi = std::max(hi, pos[i]); }
     const int range = std::max(hi - lo + 1, npos) + 2;
@@ -761,7 +770,7 @@ NLF_EXPORT int nlf_pool_find_anchors(nlf_ctx *ctx, const int *pos, int npos, int
     }
     {
         KLaunch k(c, P_POOL);
-        k_find_anchors_one<<<1, 32, 0, s>>>(d_pos, npos, res, min_count, min_dis_bp, d_order, d_ws, range, d_out, d_n);
+        k_find_anchors_one<<<1, 32, 0, s>>>(d_pos, npos, res, min_count, min_dis_bp, wlen_bp, d_order, d_ws, range, d_out, d_n);
     }
     NLF_CUDA(cudaGetLastError());
     int n = 0;

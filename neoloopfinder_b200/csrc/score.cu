@@ -32,7 +32,7 @@ using namespace nlf;
 //   featT [group][F][32] fp32  features of 32 scored pixels (slots group*32 .. +31, densely packed in
 //                              the order the feature kernel's tiles claim them), feature-major so that
 //                              the forest kernel's per-lane column is bank-conflict free
-//   pix   [slot]               {job, (x << 16) | d} of the pixel in that slot
+//   pix   [slot]               {job, (x << dshift) | d} of the pixel in that slot (dshift bits hold any d <= upper)
 //   nanmask [group]            bit l set: slot group*32+l has NaN features
 // ---------------------------------------------------------------------------------------------
 struct JobDev {
@@ -50,9 +50,10 @@ struct JobDev {
     int job;
     int n;
     int ntx;            // number of x tiles
+    int dshift;         // PixRef packing: smallest s with (1 << s) > upper; rows are limited to 2^(32-s) per job
 };
 
-// pixel behind feature slot s: .x = job, .y = (matrix row x << 16) | diagonal d
+// pixel behind feature slot s: .x = job, .y = (matrix row x << JobDev::dshift) | diagonal d
 typedef uint2 PixRef;
 
 __constant__ double c_gw[16];   // gaussian weights, radius 4: c_gw[0..8]
@@ -559,7 +560,7 @@ k_features(const JobDev *__restrict__ jobs, const int *__restrict__ tile_base, i
             // general forest kernel, which implements sklearn's missing_go_to_left routing
             if (f_nan) atomicOr(&nanmask[my_slot >> 5], 1u << (my_slot & 31u));
             if (warp == 0) {
-                pix[my_slot] = make_uint2((unsigned)job, ((unsigned)x << 16) | (unsigned)(d0 + lane));
+                pix[my_slot] = make_uint2((unsigned)job, ((unsigned)x << J.dshift) | (unsigned)(d0 + lane));
                 if (J.slot) J.slot[(size_t)x * ndp + (d0 + lane - dlo)] = (int)(slot_base + my_slot);
             }
         }
@@ -623,7 +624,7 @@ k_forest(ForestDev fr, const PixRef *__restrict__ pix, const float *__restrict__
             }
             const PixRef px = pix[slot];
             const JobDev J = jobs[px.x];
-            J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T);
+            J.prob[(size_t)(px.y >> J.dshift) * ndp + ((int)(px.y & ((1u << J.dshift) - 1u)) - dlo)] = __ddiv_rn(acc, (double)T);
         }
         __syncwarp();
     }
@@ -746,7 +747,7 @@ k_forest_dyn(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off,
                 if (last) {
                     const PixRef px = pix[g * 32u + lane];
                     const JobDev J = jobs[px.x];
-                    J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T_total);
+                    J.prob[(size_t)(px.y >> J.dshift) * ndp + ((int)(px.y & ((1u << J.dshift) - 1u)) - dlo)] = __ddiv_rn(acc, (double)T_total);
                 } else {
                     accbuf[(size_t)g * 32 + lane] = acc;
                 }
@@ -949,7 +950,7 @@ k_forest_pipe(const uint2 *__restrict__ nodes2, const int *__restrict__ tree_off
                 if (last) {
                     const PixRef px = pix[g * 32u + lane];
                     const JobDev J = jobs[px.x];
-                    J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T_total);
+                    J.prob[(size_t)(px.y >> J.dshift) * ndp + ((int)(px.y & ((1u << J.dshift) - 1u)) - dlo)] = __ddiv_rn(acc, (double)T_total);
                 } else {
                     accbuf[(size_t)g * 32 + lane] = acc;
                 }
@@ -1120,7 +1121,7 @@ k_forest_one(Forest3Dev fr, int F, const PixRef *__restrict__ pix, const unsigne
                     acc = __dadd_rn(acc, SM_F64(o_leaf + 8u * (unsigned)SM_U16(lid + 64u * (unsigned)tt)));
                 const PixRef px = pix[g * 32u + lane];
                 const JobDev J = jobs[px.x];
-                J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)T);
+                J.prob[(size_t)(px.y >> J.dshift) * ndp + ((int)(px.y & ((1u << J.dshift) - 1u)) - dlo)] = __ddiv_rn(acc, (double)T);
             }
             SM_U32(o_cnt + buf * 128u + (unsigned)lane * 4u) = 0u;
             __syncwarp();
@@ -1170,7 +1171,7 @@ __global__ void k_forest_nan(ForestDev fr, const PixRef *__restrict__ pix, const
         }
         const PixRef px = pix[slot];
         const JobDev J = jobs[px.x];
-        J.prob[(size_t)(px.y >> 16) * ndp + ((int)(px.y & 0xffffu) - dlo)] = __ddiv_rn(acc, (double)fr.n_trees);
+        J.prob[(size_t)(px.y >> J.dshift) * ndp + ((int)(px.y & ((1u << J.dshift) - 1u)) - dlo)] = __ddiv_rn(acc, (double)fr.n_trees);
     }
 }
 
@@ -1845,6 +1846,15 @@ static cudaError_t wait_inputs(nlf_batch *b)
     return cudaStreamWaitEvent(b->ctx->stream, b->ev_inputs, 0);
 }
 
+// PixRef packs (row << dshift) | diagonal in 32 bits
+static int dshift_of(const nlf_batch *b)
+{
+    int s = 1;
+    while ((1 << s) <= b->upper) s++;
+    return s;
+}
+static int max_rows(const nlf_batch *b) { return (int)std::min<long long>((1LL << (32 - dshift_of(b))) - 1, 1LL << 24); }
+
 static int check_can_add(nlf_batch *b)
 {
     if (b->scored || b->prepared) return fail(NLF_ERR_STATE, "batch already prepared/scored: add matrices first");
@@ -1855,7 +1865,7 @@ static int check_can_add(nlf_batch *b)
 NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
 {
     if (!b || !G || n <= 0) return fail(NLF_ERR_ARG, "nlf_batch_add_dense: bad arguments");
-    if (n > 65535) return fail(NLF_ERR_ARG, "dense input limited to n <= 65535 (use the band input), got %d", n);
+    if (n > 65535) return fail(NLF_ERR_ARG, "dense input limited to n <= 65535 (use the band or the pixel-table input), got %d", n);
     int rc = check_can_add(b);
     if (rc) return rc;
     nlf_ctx *c = b->ctx;
@@ -1895,7 +1905,7 @@ NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
 NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int pitch)
 {
     if (!b || !band || n <= 0 || pitch <= 0) return fail(NLF_ERR_ARG, "nlf_batch_add_band: bad arguments");
-    if (n > 65535) return fail(NLF_ERR_ARG, "band input limited to n <= 65535 rows per job, got %d (shard the chromosome)", n);
+    if (n > max_rows(b)) return fail(NLF_ERR_ARG, "band input limited to %d rows per job at upper=%d, got %d", max_rows(b), b->upper, n);
     int rc = check_can_add(b);
     if (rc) return rc;
     nlf_ctx *c = b->ctx;
@@ -1943,7 +1953,7 @@ NLF_EXPORT int nlf_batch_add_pixels(nlf_batch *b, nlf_pixels *px, int balance, l
     if (!b || !px || !n_kept || lo < 0 || hi <= lo) return fail(NLF_ERR_ARG, "nlf_batch_add_pixels: bad arguments");
     if (px->ctx != b->ctx) return fail(NLF_ERR_ARG, "nlf_batch_add_pixels: pixel table lives on another context");
     if (hi > px->nbins) return fail(NLF_ERR_ARG, "nlf_batch_add_pixels: bins [%lld,%lld) outside [0,%lld)", lo, hi, px->nbins);
-    if (hi - lo > 65535) return fail(NLF_ERR_ARG, "band input limited to n <= 65535 rows per job, got %lld (shard the chromosome)", hi - lo);
+    if (hi - lo > max_rows(b)) return fail(NLF_ERR_ARG, "band input limited to %d rows per job at upper=%d, got %lld", max_rows(b), b->upper, hi - lo);
     int rc = check_can_add(b);
     if (rc) return rc;
     nlf_ctx *c = b->ctx;
@@ -2274,6 +2284,7 @@ static int upload_jobs(nlf_batch *b, int w, int tx = 0)
         d.don_count = b->d_counts + (size_t)NLF_MAX_JOBS * 4;
         d.don_cap = b->don_cap;
         d.job = k;
+        d.dshift = dshift_of(b);
         d.n = j.n;
         d.ntx = (j.n + TX - 1) / TX;
         tb[k] = tiles;
@@ -2850,6 +2861,28 @@ NLF_EXPORT int nlf_batch_getwindow(nlf_batch *b, int job, const int *xi, const i
     NLF_CUDA(cudaFreeAsync(d_pass, c->stream));
     NLF_CUDA(cudaFreeAsync(d_fea, c->stream));
     NLF_CUDA(cudaFreeAsync(d_exp, c->stream));
+    return NLF_OK;
+}
+
+NLF_EXPORT int nlf_batch_rethreshold(nlf_batch *b, double thre)
+{
+    if (!b) return fail(NLF_ERR_ARG, "nlf_batch_rethreshold: NULL batch");
+    if (!b->scored) return fail(NLF_ERR_STATE, "batch not scored yet");
+    nlf_ctx *c = b->ctx;
+    NLF_CUDA(cudaSetDevice(c->device));
+    const int nj = (int)b->jobs.size();
+    if (nj == 0) return NLF_OK;
+    // counts[k] = {candidates, scored, donuts, -}: keep the candidates, rebuild the other two and the Donut list
+    NLF_CUDA(cudaMemset2DAsync(b->d_counts + 1, 4 * sizeof(unsigned long long), 0, 2 * sizeof(unsigned long long), (size_t)nj, c->stream));
+    NLF_CUDA(cudaMemsetAsync(b->d_counts + (size_t)NLF_MAX_JOBS * 4, 0, sizeof(unsigned long long), c->stream));
+    {
+        KLaunch k(c, P_THRESH);
+        dim3 grid(64, nj);
+        k_threshold<<<grid, 256, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->W, b->pitch, b->ndp, thre);
+    }
+    NLF_CUDA(cudaGetLastError());
+    b->counted = false;
+    b->donuts_cached = false;
     return NLF_OK;
 }
 

@@ -250,6 +250,11 @@ class ScoreBatch:
         self._counts = None
         self._keepalive.clear()
 
+    def rethreshold(self, thre: float):
+        """Another probability threshold on the probabilities already in HBM (no re-scoring)."""
+        check(_lib.load().nlf_batch_rethreshold(self.h, float(thre)))
+        self._counts = None
+
     def reset(self):
         """Forget the results, keep the matrices in HBM (lets the scoring path run again)."""
         check(_lib.load().nlf_batch_reset(self.h))

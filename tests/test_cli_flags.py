@@ -61,7 +61,7 @@ def test_neoloop_caller_flags(monkeypatch):
     mine = _table(_mine(cli, monkeypatch))
     for key, spec in ref.items():
         assert mine.get(key) == spec, key
-    assert {k for k in mine if k not in ref} == {("--model",), ("--gpus",)}          # documented additions
+    assert {k for k in mine if k not in ref} == {("--model",), ("--gpus",), ("--genome-wide",), ("--chroms",)}   # documented additions
 
 
 def test_assemble_complexsvs_flags(monkeypatch):

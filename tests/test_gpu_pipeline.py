@@ -322,3 +322,23 @@ def test_calculate_expected_gpu_equals_port():
     want = pyport.calculate_expected(arr, list(small), maxdis=600000, balance="weight")
     got = calculate_expected(arr, list(small), maxdis=600000, balance="weight")
     assert all(got[k] == want[k] for k in want) and len(got) == len(want) == 61
+
+
+def test_multi_sample_batch_equals_per_sample_calls():
+    """BASELINE.json configs[4]: several samples in one run give, per sample, what call_resolution gives alone."""
+    from neoloopfinder_b200.cli import call_resolution
+    from neoloopfinder_b200.multisample import call_samples
+    from neoloopfinder_b200.synth import SMALL_CHROMSIZES, analytic_expected, make_workload
+    model = os.path.join(GOLDEN, "forest_w6.joblib")
+    samples = {}
+    for k in range(3):
+        clr, lines = make_workload("simple", res=10000, seed=900 + k, n_assemblies=3, chromsizes=SMALL_CHROMSIZES, span=800000)
+        samples["S%d" % k] = {"clr": clr, "assemblies": lines, "model": model, "expected": analytic_expected(clr)}
+    stats = {}
+    got = call_samples(samples, 800000, "sweight", 0.5, 2, False, devices=[0], stats=stats)
+    n = 0
+    for name, s in samples.items():
+        want = call_resolution(s["clr"], s["assemblies"], 800000, "sweight", 0.5, 2, False, model, s["expected"], devices=[0])
+        assert got[name] == want, name
+        n += sum(len(r) for r in want if r)
+    assert n > 0 and stats["scored"] > 10000

@@ -86,3 +86,24 @@ def test_lpt_is_a_balanced_disjoint_cover():
         assert flat == list(range(len(w)))
         loads = [sum(w[k] for k in s) for s in shards]
         assert max(loads) - min(loads) <= max(w)
+
+
+def test_multi_sample_units_are_dealt_once_and_evenly():
+    """BASELINE.json configs[4]: (sample, assembly) units of many samples over 8 workers -- every unit exactly once,
+    loads within one unit's weight of each other, deterministic."""
+    from neoloopfinder_b200.multisample import shard_sample_units
+    from neoloopfinder_b200.sharding import assembly_weight
+    from neoloopfinder_b200.synth import make_workload
+
+    samples = {}
+    for k in range(6):
+        clr, lines = make_workload("simple" if k % 2 else "complex", res=10000, seed=50 + k, n_assemblies=7 + k)
+        samples["S%d" % k] = {"clr": clr, "assemblies": lines}
+    shards = shard_sample_units(samples, 3_000_000, 8)
+    flat = [u for s in shards for u in s]
+    want = [(n, ID) for n, s in samples.items() for ID in s["assemblies"]]
+    assert sorted(flat) == sorted(want) and len(set(flat)) == len(want)
+    assert shards == shard_sample_units(samples, 3_000_000, 8)
+    w = {(n, ID): assembly_weight(s["assemblies"][ID], 3_000_000, 10000) for n, s in samples.items() for ID in s["assemblies"]}
+    loads = [sum(w[u] for u in s) for s in shards]
+    assert max(loads) - min(loads) <= max(w.values())
