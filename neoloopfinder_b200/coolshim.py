@@ -133,14 +133,14 @@ class _BinsSelector:
             "chrom": np.array([c] * n, dtype=object),
             "start": start,
             "end": end,
-            "weight": self._clr._weights(c, lo, hi, "weight"),
-            "sweight": self._clr._weights(c, lo, hi, "sweight"),
         }
+        for col in self._clr.weight_columns():          # a column the map does not have is a KeyError, as in cooler
+            cols[col] = self._clr._weights(c, lo, hi, col)
         return _Frame(cols)
 
     def __getitem__(self, key):
         # whole bin table (only used with [:])
-        cols = {"chrom": [], "start": [], "end": [], "weight": [], "sweight": []}
+        cols = {k: [] for k in ("chrom", "start", "end") + tuple(self._clr.weight_columns())}
         for c in self._clr.chromnames:
             fr = self.fetch(c)
             for k in cols:
@@ -224,8 +224,18 @@ class _CoolerBase:
     def _nbins(self, c) -> int:
         return int(math.ceil(self._chromsizes[c] / self.binsize))
 
+    def weight_columns(self) -> Tuple[str, ...]:
+        return ("weight", "sweight")
+
     def _bin_extent(self, region) -> Tuple[str, int, int]:
         c, start, end = parse_region(region, self._chromsizes)
+        # cooler.util.parse_region: malformed bounds are errors, not empty selections
+        if c not in self._chromsizes:
+            raise ValueError("Unknown sequence label: {}".format(c))
+        if end < start:
+            raise ValueError("End cannot be less than start")
+        if start < 0 or end > self._chromsizes[c]:
+            raise ValueError("Genomic region out of bounds: [{}, {})".format(start, end))
         res = self.binsize
         lo = start // res
         hi = int(math.ceil(end / res))
@@ -537,9 +547,12 @@ class ArrayCooler(_CoolerBase):
             s += np.triu(B).sum() if c1 == c2 else B.sum()
         return {"sum": int(s), "nnz": int(sum((b != 0).sum() for b in self._blocks.values()))}
 
+    def weight_columns(self):
+        return tuple(self._w)
+
     def _weights(self, c, lo, hi, col):
         if col not in self._w:
-            col = "weight"
+            raise KeyError(col)                      # cooler: no such balancing column in the bin table
         return np.array(self._w[col][c][lo:hi], dtype=np.float64, copy=True)
 
     def _raw_block(self, c1, lo1, hi1, c2, lo2, hi2):
@@ -725,9 +738,12 @@ class PixelCooler(_CoolerBase):
             return self._info
         return {"sum": int(self.count.sum(dtype=np.int64)), "nnz": int(self.count.size)}
 
+    def weight_columns(self):
+        return tuple(self._w)
+
     def _weights(self, c, lo, hi, col):
         if col not in self._w:
-            col = "weight"
+            raise KeyError(col)                      # cooler: no such balancing column in the bin table
         o = self._offsets[c]
         return np.array(self._w[col][o + lo:o + hi], dtype=np.float64, copy=True)
 
@@ -765,7 +781,7 @@ class PixelCooler(_CoolerBase):
         if col in (True, False, None):
             col = "weight"                # balance=True / raw counts: the bias column of the reference
         if col not in self._w:
-            col = "weight"
+            raise KeyError(col)
         key = (os.getpid(), ctx.device, col)
         if key not in self._device:
             self._device[key] = DevicePixels(self.bin1_offset, self.bin2, self.count, self._w[col], ctx)

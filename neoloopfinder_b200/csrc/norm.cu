@@ -159,6 +159,18 @@ __global__ void k_dense_out(const double *__restrict__ M, int n, const int *__re
     out[(size_t)i * nk + j] = scaled_value(M, n, blk, op, val, nblk, r, c);
 }
 
+// a CUDA failure after the assembly object exists hands its device memory back before reporting
+#define NLF_CUDA_A(call)                                                                            \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                     \
+            nlf_assembly_destroy(a);                                                                \
+            return nlf::fail(NLF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                             cudaGetErrorString(e__));                                              \
+        }                                                                                           \
+    } while (0)
+
 // block table checks + device allocations shared by the two constructors
 static int assembly_alloc(nlf_ctx *ctx, int n, const int *blk_lo, const int *blk_hi, int nblk, nlf_assembly **out)
 {
@@ -180,19 +192,19 @@ static int assembly_alloc(nlf_ctx *ctx, int n, const int *blk_lo, const int *blk
     a->blo.assign(blk_lo, blk_lo + nblk);
     a->bhi.assign(blk_hi, blk_hi + nblk);
     cudaStream_t s = ctx->stream;
-    NLF_CUDA(cudaMallocAsync(&a->d_M, sizeof(double) * (size_t)n * n, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_bias, sizeof(double) * n, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_blk, sizeof(int) * n, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_op, sizeof(int) * nblk * nblk, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_val, sizeof(double) * nblk * nblk, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_kept, sizeof(int) * n, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_blo, sizeof(int) * nblk, s));
-    NLF_CUDA(cudaMallocAsync(&a->d_bhi, sizeof(int) * nblk, s));
-    NLF_CUDA(cudaMemcpyAsync(a->d_blo, blk_lo, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(a->d_bhi, blk_hi, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(a->d_blk, blk.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemsetAsync(a->d_op, 0, sizeof(int) * nblk * nblk, s));
-    NLF_CUDA(cudaMemsetAsync(a->d_val, 0, sizeof(double) * nblk * nblk, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_M, sizeof(double) * (size_t)n * n, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_bias, sizeof(double) * n, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_blk, sizeof(int) * n, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_op, sizeof(int) * nblk * nblk, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_val, sizeof(double) * nblk * nblk, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_kept, sizeof(int) * n, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_blo, sizeof(int) * nblk, s));
+    NLF_CUDA_A(cudaMallocAsync(&a->d_bhi, sizeof(int) * nblk, s));
+    NLF_CUDA_A(cudaMemcpyAsync(a->d_blo, blk_lo, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
+    NLF_CUDA_A(cudaMemcpyAsync(a->d_bhi, blk_hi, sizeof(int) * nblk, cudaMemcpyHostToDevice, s));
+    NLF_CUDA_A(cudaMemcpyAsync(a->d_blk, blk.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA_A(cudaMemsetAsync(a->d_op, 0, sizeof(int) * nblk * nblk, s));
+    NLF_CUDA_A(cudaMemsetAsync(a->d_val, 0, sizeof(double) * nblk * nblk, s));
     // (pageable sources are staged before cudaMemcpyAsync returns: `blk` may go out of scope)
     *out = a;
     return NLF_OK;
@@ -207,8 +219,8 @@ NLF_EXPORT int nlf_assembly_create(nlf_ctx *ctx, const double *M, int n, const d
     int rc = assembly_alloc(ctx, n, blk_lo, blk_hi, nblk, &a);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
-    NLF_CUDA(cudaMemcpyAsync(a->d_M, M, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s));
-    NLF_CUDA(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA_A(cudaMemcpyAsync(a->d_M, M, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s));
+    NLF_CUDA_A(cudaMemcpyAsync(a->d_bias, bias, sizeof(double) * n, cudaMemcpyHostToDevice, s));
     *out = a;
     return NLF_OK;
 }

@@ -64,8 +64,8 @@ __constant__ double c_gw[16];   // gaussian weights, radius 4: c_gw[0..8]
 __global__ void k_bandify(const double *__restrict__ G, int n, int bw, int pitch, double *__restrict__ band,
                           int *__restrict__ status)
 {
-    int r = blockIdx.y;
-    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.x;                                   // rows in grid.x: a job may have more than 65 535 of them
+    int d = blockIdx.y * blockDim.x + threadIdx.x;
     if (d >= pitch) return;
     double v = 0.0;
     if (d < bw && r + d < n) {
@@ -85,8 +85,8 @@ __global__ void k_bandify(const double *__restrict__ G, int n, int bw, int pitch
 __global__ void k_band_copy(const double *__restrict__ src, int n, int src_pitch, int bw, int pitch,
                             double *__restrict__ band)
 {
-    int r = blockIdx.y;
-    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.x;
+    int d = blockIdx.y * blockDim.x + threadIdx.x;
     if (d >= pitch) return;
     double v = 0.0;
     if (d < bw && d < src_pitch && r + d < n) {
@@ -1201,31 +1201,39 @@ __global__ void k_forest_rows(ForestDev fr, const float *__restrict__ X, long lo
 // K9 threshold: count scored pixels, append pixels with proba >= thre (callers.py:625-628)
 // with their contact value M[i,j].  Also counts the candidates of get_candidates.
 // =============================================================================================
-__global__ void k_threshold(const JobDev *__restrict__ jobs, int lower, int upper, int W, int pitch, int ndp,
-                            double thre)
+__global__ void __launch_bounds__(256) k_threshold(const JobDev *__restrict__ jobs, int lower, int upper, int W, int pitch, int ndp,
+                                                   double thre)
 {
+    // HBM-bound scan of the probability plane: one warp per matrix row, 128-bit loads (a row of `prob` starts on a
+    // 256-byte boundary), no index division; the rare pixels above the threshold are appended with one atomic each.
     const JobDev J = jobs[blockIdx.y];
     if (*J.status != 0) return;
     const int dlo = max(lower, W + 2);
     const int nd = upper - dlo + 1;
-    const long long total = (long long)J.n * nd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     unsigned long long scored = 0, donuts = 0;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total;
-         k += (long long)gridDim.x * blockDim.x) {
-        int x = (int)(k / nd), dd = (int)(k % nd);
-        double p = J.prob[(size_t)x * ndp + dd];
-        if (p == p) {
-            scored++;
-            if (p >= thre) {
-                donuts++;
-                unsigned long long pos = atomicAdd(J.don_count, 1ULL);
-                if ((long long)pos < J.don_cap) {
-                    int d = dlo + dd;
-                    J.don_job[pos] = J.job;
-                    J.don_i[pos] = x;
-                    J.don_j[pos] = x + d;
-                    J.don_p[pos] = p;
-                    J.don_v[pos] = J.band[(size_t)x * pitch + d];
+    for (int x = blockIdx.x * nwarp + warp; x < J.n; x += gridDim.x * nwarp) {
+        const double2 *row = reinterpret_cast<const double2 *>(J.prob + (size_t)x * ndp);
+        for (int k = lane; 2 * k < nd; k += 32) {
+            const double2 pp = row[k];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int dd = 2 * k + h;
+                const double p = h ? pp.y : pp.x;
+                if (dd < nd && p == p) {
+                    scored++;
+                    if (p >= thre) {
+                        donuts++;
+                        unsigned long long pos = atomicAdd(J.don_count, 1ULL);
+                        if ((long long)pos < J.don_cap) {
+                            const int d = dlo + dd;
+                            J.don_job[pos] = J.job;
+                            J.don_i[pos] = x;
+                            J.don_j[pos] = x + d;
+                            J.don_p[pos] = p;
+                            J.don_v[pos] = J.band[(size_t)x * pitch + d];
+                        }
+                    }
                 }
             }
         }
@@ -1235,7 +1243,7 @@ __global__ void k_threshold(const JobDev *__restrict__ jobs, int lower, int uppe
         scored += __shfl_down_sync(0xffffffffu, scored, o);
         donuts += __shfl_down_sync(0xffffffffu, donuts, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (scored) atomicAdd(&J.counts[1], scored);
         if (donuts) atomicAdd(&J.counts[2], donuts);
     }
@@ -1251,20 +1259,32 @@ __device__ __forceinline__ bool is_candidate(const JobDev &J, int x, int d, int 
     return __ddiv_rn(J.band[(size_t)x * pitch + d], e) > 0;
 }
 
-__global__ void k_count_candidates(const JobDev *__restrict__ jobs, int lower, int upper, int pitch)
+__global__ void __launch_bounds__(256) k_count_candidates(const JobDev *__restrict__ jobs, int lower, int upper, int pitch)
 {
+    // HBM-bound scan of the band: one warp per matrix row, 128-bit loads (pitch is a multiple of 4 doubles and the
+    // band is 256-byte aligned), the exact division only for cells that are not zero.
     const JobDev J = jobs[blockIdx.y];
     if (*J.status != 0) return;
-    const int nd = upper - lower + 1;
-    const long long total = (long long)J.n * nd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = J.n;
     unsigned long long c = 0;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total;
-         k += (long long)gridDim.x * blockDim.x) {
-        int x = (int)(k / nd), d = lower + (int)(k % nd);
-        c += is_candidate(J, x, d, pitch);
+    for (int x = blockIdx.x * nwarp + warp; x < n; x += gridDim.x * nwarp) {
+        const double2 *row = reinterpret_cast<const double2 *>(J.band + (size_t)x * pitch);
+        for (int k = (lower >> 1) + lane; 2 * k <= upper; k += 32) {
+            const double2 vv = row[k];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int d = 2 * k + h;
+                const double v = h ? vv.y : vv.x;
+                if (d >= lower && d <= upper && v != 0.0 && x + d < n && n - d > 1) {
+                    const double e = J.e[d];
+                    c += (e > 0) && (__ddiv_rn(v, e) > 0);
+                }
+            }
+        }
     }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&J.counts[0], c);
+    if (lane == 0 && c) atomicAdd(&J.counts[0], c);
 }
 
 // Ordered (diagonal-major, row-ascending) listing used by the API/test accessors.
@@ -1892,7 +1912,7 @@ NLF_EXPORT int nlf_batch_add_dense(nlf_batch *b, const double *G, int n)
     }
     {
         KLaunch k(c, P_BANDIFY, cs);
-        dim3 grid((b->pitch + 127) / 128, n);
+        dim3 grid(n, (b->pitch + 127) / 128);
         k_bandify<<<grid, 128, 0, cs>>>(d_dense, n, b->bw, b->pitch, j.d_band, b->d_status + b->jobs.size());
     }
     NLF_CUDA(cudaGetLastError());
@@ -1919,7 +1939,7 @@ NLF_EXPORT int nlf_batch_add_band(nlf_batch *b, const double *band, int n, int p
     NLF_CUDA(cudaMemcpyAsync(d_src, band, sizeof(double) * (size_t)n * pitch, cudaMemcpyHostToDevice, cs));
     {
         KLaunch k(c, P_BANDIFY, cs);
-        dim3 grid((b->pitch + 127) / 128, n);
+        dim3 grid(n, (b->pitch + 127) / 128);
         k_band_copy<<<grid, 128, 0, cs>>>(d_src, n, pitch, b->bw, b->pitch, j.d_band);
     }
     NLF_CUDA(cudaGetLastError());

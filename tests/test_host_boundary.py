@@ -68,3 +68,28 @@ def test_expected_tables_come_from_the_reference_data_folder(monkeypatch, res):
     name = {5000: "5k", 10000: "10k", 25000: "25k"}[res]
     want = joblib.load(os.path.join(folder, "gm.insitu.expected.%s.pkl" % name))
     assert fu.expected == want and len(want) in (1000, 500, 200)
+
+
+def test_missing_weight_column_and_bad_regions_raise_like_cooler():
+    """cooler raises KeyError for a balancing column the bin table lacks and ValueError for inverted or
+    out-of-bounds regions; the stand-ins must not fall back to another column or clamp silently."""
+    from neoloopfinder_b200.coolshim import ArrayCooler, PixelCooler
+    sizes = {"chr1": 1_000_000}
+    n = 100
+    w = np.full(n, 0.1)
+    px = PixelCooler(10000, sizes, np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32), np.ones(n, np.int32), {"weight": w})
+    ar = ArrayCooler(10000, sizes, {("chr1", "chr1"): np.eye(n)}, {"weight": {"chr1": w}})
+    for clr in (px, ar):
+        assert clr.matrix(balance="weight").fetch(("chr1", 0, 200000)).shape == (20, 20)
+        with pytest.raises(KeyError):
+            clr.matrix(balance="sweight").fetch(("chr1", 0, 200000))
+        with pytest.raises(KeyError):
+            clr.bins().fetch(("chr1", 0, 200000))["sweight"]
+        with pytest.raises(ValueError):
+            clr.matrix(balance=False).fetch(("chr1", 300000, 200000))
+        with pytest.raises(ValueError):
+            clr.bins().fetch(("chr1", 0, 1_000_001))
+        with pytest.raises(ValueError):
+            clr.bins().fetch(("chr7", 0, 10))
+    with pytest.raises(KeyError):
+        px.device_pixels(object(), "sweight")
