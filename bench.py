@@ -47,31 +47,47 @@ WORKLOADS = {
     "cfg3": (5000, "complex", 192, "cfg3 (BASELINE.json configs[2]): synthetic 5 kb hg38-sized map, %d complex assemblies "
                                    "(chains of 2-5 SVs) in total"),
     "cfg2": (10000, "simple", 50, "cfg2 (BASELINE.json configs[1]): synthetic 10 kb hg38-sized map, %d simple SV assemblies in total"),
+    "cfg5": (10000, "simple", 50, "cfg5 (BASELINE.json configs[4]): multi-sample batch, SAMPLES synthetic 10 kb hg38-sized maps x %d simple "
+                                  "SV assemblies each, (sample, assembly) units dealt to the GPUs"),
+    "cfg4": (5000, "genome", 23, "cfg4 (BASELINE.json configs[3]): genome-wide 5 kb call, %d chromosomes of a synthetic hg38-sized map as "
+                                 "trivial assemblies"),
 }
 CROP = 700              # bins of a parity / CPU-baseline matrix (about 15-20 s of one core per matrix at 5 kb)
 CPU_SLICE = 50000       # candidates per work unit of the reference arm (about 13 s of one core)
 
 
 class Workload:
-    def __init__(self, name, n_assemblies):
+    def __init__(self, name, n_assemblies, n_samples=0):
         self.name = name
         self.res, self.kind, default_n, self.what = WORKLOADS[name]
         self.n = n_assemblies or default_n
+        self.n_samples = (n_samples or 50) if name == "cfg5" else 1
+        self.what = self.what.replace("SAMPLES", str(self.n_samples))
 
-    def build(self):
+    def build(self, sample=0):
         from neoloopfinder_b200.synth import analytic_expected, make_workload
-        clr, lines = make_workload(self.kind, res=self.res, seed=SEED, n_assemblies=self.n, span=SPAN)
+        clr, lines = make_workload(self.kind, res=self.res, seed=SEED + sample, n_assemblies=self.n, span=SPAN)
         return clr, lines, analytic_expected(clr)
+
+    def build_samples(self):
+        """{sample name: {clr, assemblies, expected}} -- one sample for cfg2 / cfg3, n_samples seeds for cfg5."""
+        out = {}
+        for k in range(self.n_samples):
+            clr, lines, expected = self.build(k)
+            out["S%d" % k] = {"clr": clr, "assemblies": lines, "expected": expected}
+        return out
 
     def config(self, n_gpus):
         return {
             "workload": "%s, 3 Mb span, prob %.2f" % (self.what % self.n, THRESHOLD),
-            "resolution": self.res, "assemblies_total": self.n, "span_bp": SPAN,
+            "resolution": self.res, "assemblies_total": self.n * self.n_samples, "samples": self.n_samples, "span_bp": SPAN,
             "forest": "synthetic sklearn RandomForest, 100 trees, depth<=20, 32048 nodes, 169 features (tests/golden/forest_w6.joblib)",
             "expected": "analytic A/(d+1) of the procedural map",
             "source": "regional pixel table (cooler layout) resident in HBM; assemblies built on the device",
-            "sharding": ("one fixed assembly list dealt to %d ranks by sharding.shard_ids (LPT on estimated pixels), "
-                         "one process per GPU, no collective on the data path" % n_gpus) if n_gpus > 1 else "single GPU",
+            "sharding": ("one fixed list of %s dealt to %d ranks by %s (LPT on estimated pixels), one process per GPU, no "
+                         "collective on the data path" % (("(sample, assembly) units", n_gpus, "multisample.shard_sample_units")
+                                                          if self.n_samples > 1 else ("assemblies", n_gpus, "sharding.shard_ids")))
+                        if n_gpus > 1 else "single GPU",
             "cache": "L2 flushed (256 MB memset) at the start of every step",
         }
 
@@ -235,6 +251,9 @@ def run_reference_arm(args, wl, rank):
         return
     from joblib import Parallel, delayed
     cores = os.cpu_count() or 1
+    config = wl.config(args.gpus)
+    if wl.name == "cfg4":
+        wl = Workload("cfg3", 0)          # the port has no banded input: its pixels/s is measured on 5 kb assembly matrices
     clr, lines, expected = wl.build()
     n_mats = 4 if wl.name == "cfg3" else 6
     todo = [(clr, ln, expected) for ln in list(lines.values())[:n_mats + 2]]
@@ -264,12 +283,125 @@ def run_reference_arm(args, wl, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.config(args.gpus),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def run_genome_wide(args, wl, rank, world, local_rank):
+    """cfg4: every chromosome of a synthetic hg38-sized 5 kb map as a trivial assembly (genome.call_chromosomes), the
+    chromosomes dealt to the ranks by LPT on their bin counts.  A step is one whole call from the pixel table resident
+    in HBM (gap removal and bands on the device, K5-K10, coordinates); e2e also uploads the rank's pixel table from
+    pinned host memory inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; neoloopfinder_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from neoloopfinder_b200 import _lib
+    from neoloopfinder_b200.coolshim import HG38_CHROMSIZES, PixelCooler, SyntheticCooler
+    from neoloopfinder_b200.forest import load_forest
+    from neoloopfinder_b200.genome import _Subset, call_chromosomes
+    from neoloopfinder_b200.scoring import DevicePixels
+    from neoloopfinder_b200.sharding import lpt_shards
+    from neoloopfinder_b200.synth import analytic_expected
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    ctx = _lib.Context.get(local_rank)
+    forest = load_forest(MODEL, ctx)
+    names = args.chroms.split(",") if args.chroms else [c for c in HG38_CHROMSIZES if c != "chrY"]
+    sizes = {c: HG38_CHROMSIZES[c] for c in names}
+    mine = [names[k] for k in sorted(lpt_shards([float(sizes[c]) for c in names], world)[rank])]
+    clr = SyntheticCooler(binsize=wl.res, chromsizes=sizes, seed=404, amplitude=255.0 * wl.res / 10000.0)
+    expected = analytic_expected(clr)
+    t0 = time.perf_counter()
+    px = PixelCooler.from_cooler(_Subset(clr, mine), band_bins=449, trans=False) if mine else None
+    prep_s = time.perf_counter() - t0
+
+    def one_pass(stats=None):
+        return call_chromosomes(px, mine, forest, expected, THRESHOLD, 2, False, "sweight", ctx, stats, 400) if mine else {}
+
+    def sync():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    st = {}
+    launches0 = ctx.launch_count()
+    calls = one_pass(st)                                        # uploads the table, warms the buffers
+    launches_per_pass = ctx.launch_count() - launches0
+    for _ in range(max(2, args.warmup - 1)):
+        one_pass()
+    steps = max(1, args.steps)
+    sync()
+    ctx.timer_start()
+    for _ in range(steps):
+        ctx.l2_flush()
+        one_pass()
+    ms = reduce(max(ctx.timer_stop(), 0.0), dist.ReduceOp.MAX) / steps
+    sync()
+    # end to end: host pixel table (pinned) -> HBM -> calls, every step
+    ms_e, h2d = 0.0, 0
+    if mine:
+        pin = {k: torch.from_numpy(a).pin_memory() for k, a in (("off", px.bin1_offset), ("b2", px.bin2), ("cnt", px.count),
+                                                                 ("w", px._w["sweight"]))}
+        h2d = int(sum(t.numel() * t.element_size() for t in pin.values()))
+        key = (os.getpid(), ctx.device, "sweight")
+
+        def e2e_pass():
+            old = px._device.pop(key, None)
+            if old is not None:
+                old.close()
+            px._device[key] = DevicePixels(pin["off"].numpy(), pin["b2"].numpy(), pin["cnt"].numpy(), pin["w"].numpy(), ctx)
+            return one_pass()
+        e2e_pass()
+    sync()
+    ctx.timer_start()
+    for _ in range(steps):
+        ctx.l2_flush()
+        if mine:
+            e2e_pass()
+    ms_e = reduce(max(ctx.timer_stop(), 0.0), dist.ReduceOp.MAX) / steps
+    sync()
+    scored = reduce(float(st.get("scored", 0)), dist.ReduceOp.SUM)
+    bins = reduce(float(st.get("bins", 0)), dist.ReduceOp.SUM)
+    loops = reduce(float(sum(len(v[0]) for v in calls.values())), dist.ReduceOp.SUM)
+    h2d_all = reduce(float(h2d), dist.ReduceOp.SUM)
+    prep_max = reduce(prep_s, dist.ReduceOp.MAX)
+    launches_all = reduce(float(launches_per_pass), dist.ReduceOp.SUM)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": scored / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s, prob %.2f" % (wl.what % len(names), THRESHOLD), "resolution": wl.res, "chromosomes": len(names),
+                       "gap_free_bins": int(bins), "source": "banded intra-chromosomal pixel table (cooler layout, 449 diagonals) resident "
+                       "in HBM; gap removal and bands built on the device",
+                       "sharding": "chromosomes dealt to %d ranks by LPT on bin counts, no collective" % world if world > 1 else "single GPU",
+                       "cache": "L2 flushed (256 MB memset) at the start of every step"},
+            "seconds_per_genome_wide_call": ms * 1e-3,
+            "gpu_launches": int(launches_all) * steps,
+            "e2e": {"value": scored / (ms_e * 1e-3) if ms_e else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
+                    "d2h_bytes_per_step": int(25 * loops), "ms_per_step": ms_e,
+                    "what": "pixel table from pinned host memory -> HBM -> called loops, every step"},
+            "pixels": {"scored_per_step_total": int(scored), "loops_per_step_total": int(loops)},
+            "prep_seconds_max_over_ranks": {"procedural_map_to_pixel_table": prep_max},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -278,12 +410,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--assemblies", type=int, default=0, help="assemblies in TOTAL (default: 192 for cfg3, 50 for cfg2)")
+    ap.add_argument("--assemblies", type=int, default=0, help="assemblies per sample (default: 192 for cfg3, 50 for cfg2 / cfg5)")
+    ap.add_argument("--samples", type=int, default=0, help="cfg5: number of samples (default 50)")
+    ap.add_argument("--chroms", default=None, help="cfg4: comma-separated chromosomes (default: chr1..chr22, chrX)")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the cli_e2e measurement")
     args = ap.parse_args()
-    wl = Workload(args.workload, args.assemblies)
+    wl = Workload(args.workload, args.assemblies, args.samples)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -291,6 +425,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, wl, rank)
+        return
+    if wl.name == "cfg4":
+        run_genome_wide(args, wl, rank, world, local_rank)
         return
 
     import torch
@@ -302,8 +439,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from neoloopfinder_b200 import _lib
-    from neoloopfinder_b200.cli import call_assemblies
     from neoloopfinder_b200.forest import load_forest
+    from neoloopfinder_b200.multisample import call_units, shard_sample_units
     from neoloopfinder_b200.scoring import ScoreBatch, score_and_pool, score_matrices
     from neoloopfinder_b200.sharding import shard_ids
     from neoloopfinder_b200.synth import regional_pixel_cooler
@@ -332,35 +469,55 @@ def main():
     ctx = _lib.Context.get(local_rank)
     forest = load_forest(MODEL, ctx)
     t_prep = time.perf_counter()
-    clr_syn, lines, expected = wl.build()
-    ids = list(lines)
-    mine = shard_ids(ids, lines, SPAN, wl.res, world)[rank]            # the product's sharder, one fixed list
-    my_lines = {ID: lines[ID] for ID in mine}
-    clr = regional_pixel_cooler(clr_syn, my_lines, SPAN, nproc=nproc)   # this rank's part of the sample, cooler layout
+    syn = wl.build_samples()
+    if wl.n_samples == 1:
+        # one sample: the product's own sharder deals one fixed assembly list to the ranks
+        lines = syn["S0"]["assemblies"]
+        units = [("S0", ID) for ID in shard_ids(list(lines), lines, SPAN, wl.res, world)[rank]]
+    else:
+        units = shard_sample_units(syn, SPAN, world)[rank]          # (sample, assembly) units over the ranks
+    mine = {}
+    for name, ID in units:
+        mine.setdefault(name, []).append(ID)
+    expected = syn[next(iter(syn))]["expected"]                     # same analytic table for every seed
     exp_arr = np.r_[[expected[i] for i in sorted(expected)]]
+    # this rank's part of every sample it touches, as pixel tables in cooler's layout
+    samples = {}
+    for name, ids in mine.items():
+        s0 = syn[name]
+        px = regional_pixel_cooler(s0["clr"], {ID: s0["assemblies"][ID] for ID in ids}, SPAN, nproc=nproc)
+        samples[name] = {"clr": px, "assemblies": s0["assemblies"], "model": forest, "expected": s0["expected"]}
     table_s = time.perf_counter() - t_prep
 
     # ---- the product entry on this shard: warm (pixel table upload, loky workers), then timed wall clock
     cli = None
-    call_assemblies(clr, mine[:2], lines, SPAN, "sweight", THRESHOLD, 2, False, forest, expected, ctx, nproc=nproc)
+    my_cli = 0.0
+    call_units(samples, units[:2], SPAN, "sweight", THRESHOLD, 2, False, ctx, nproc)
+    for s0 in samples.values():
+        s0["clr"].device_pixels(ctx, "sweight")
     if not args.no_cli:
         st = {}
         barrier()
         t0 = time.perf_counter()
-        res_cli = call_assemblies(clr, mine, lines, SPAN, "sweight", THRESHOLD, 2, False, forest, expected, ctx, st, nproc)
+        res_cli = call_units(samples, units, SPAN, "sweight", THRESHOLD, 2, False, ctx, nproc, st)
         ctx.sync()
         my_cli = time.perf_counter() - t0
         barrier()
         cli_s = max_over_ranks(my_cli)
-        cli = {"seconds": cli_s, "assemblies": wl.n, "scored_pixels": int(sum_over_ranks(float(st.get("scored", 0)))),
+        cli = {"seconds": cli_s, "assemblies": wl.n * wl.n_samples, "scored_pixels": int(sum_over_ranks(float(st.get("scored", 0)))),
                "loops": int(sum_over_ranks(float(sum(len(r) for r in res_cli.values() if r)))),
                "host_workers_per_gpu": nproc,
-               "what": "wall time of cli.call_assemblies on every rank's shard (max over ranks): assembly from the resident "
-                       "pixel table, diagonal means, host Huber/isotonic regressions on loky workers, scoring, pooling, "
-                       "coordinates; the pixel table upload is outside"}
+               "what": "wall time of the product entry (cli.call_assemblies per sample, multisample.call_units) on every rank's "
+                       "shard, max over ranks: assembly from the resident pixel table, diagonal means, host Huber/isotonic "
+                       "regressions on loky workers, scoring, pooling, coordinates; the pixel table upload is outside"}
         cli["pixels_per_s"] = cli["scored_pixels"] / cli_s if cli_s > 0 else None
     # ---- untimed preparation with the same product path, keeping the gap-free matrices on the host
-    mats, chains = gap_free_matrices(clr, mine, lines, expected, ctx, forest, wl.res, nproc)
+    mats, chains = [], []
+    for name, ids in mine.items():
+        s0 = samples[name]
+        m, c = gap_free_matrices(s0["clr"], ids, s0["assemblies"], s0["expected"], ctx, forest, wl.res, nproc)
+        mats += m
+        chains += c
     pinned = [torch.from_numpy(G).pin_memory() for G in mats]
     host_mats = [t.numpy() for t in pinned]
     del mats
@@ -507,13 +664,15 @@ def main():
             "note": "a warp node step needs >= 3 wavefronts (4-byte feature load + 8-byte node load); %.0f node visits "
                     "per pixel on this forest" % visits,
         }
+        rows = float(sum(G.shape[0] for G in host_mats))
         band = {}
-        for k in ("diag", "threshold", "bandify"):
+        # HBM-bound band kernels: bytes they have to read per step / their CUDA-event time
+        for k, kname, nbytes in (("diag", "k_diag_means", rows * 397 * 8), ("count", "k_count_candidates", rows * 397 * 8),
+                                 ("threshold", "k_threshold", rows * 393 * 8)):
             if k in kern and kern[k]["ms_per_step"] > 0:
-                nbytes = band_bytes * (2.0 if k == "bandify" else 1.0)
-                band[k] = {"ms_per_step": kern[k]["ms_per_step"], "bytes_per_step": nbytes,
-                           "hbm_gbs": nbytes / (kern[k]["ms_per_step"] * 1e-3) / 1e9,
-                           "frac": nbytes / (kern[k]["ms_per_step"] * 1e-3) / 1e9 / hbm_peak}
+                gbs = nbytes / (kern[k]["ms_per_step"] * 1e-3) / 1e9
+                band[kname] = {"ms_per_step": kern[k]["ms_per_step"], "algorithmic_bytes_per_step": nbytes, "hbm_gbs": gbs,
+                               "frac": gbs / hbm_peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

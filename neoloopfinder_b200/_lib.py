@@ -214,4 +214,4 @@ class Context:
         return ms.value, n.value
 
 
-PROF = {"bandify": 0, "diag": 1, "feature": 2, "forest": 3, "threshold": 4, "norm": 5, "pool": 6, "score": 7}
+PROF = {"bandify": 0, "diag": 1, "feature": 2, "forest": 3, "threshold": 4, "norm": 5, "pool": 6, "score": 7, "isotonic": 8, "count": 9}

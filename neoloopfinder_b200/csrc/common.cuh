@@ -36,7 +36,7 @@ inline int fail(int code, const char *fmt, ...)
                              cudaGetErrorString(e__));                                              \
     } while (0)
 
-enum ProfClass { P_BANDIFY = 0, P_DIAG = 1, P_FEATURE = 2, P_FOREST = 3, P_THRESH = 4, P_NORM = 5, P_POOL = 6, P_SCORE = 7, P_NCLASS = 9 };
+enum ProfClass { P_BANDIFY = 0, P_DIAG = 1, P_FEATURE = 2, P_FOREST = 3, P_THRESH = 4, P_NORM = 5, P_POOL = 6, P_SCORE = 7, P_ISO = 8, P_COUNT = 9, P_NCLASS = 11 };
 // P_SCORE: the whole feature + forest region of one nlf_batch_score call (the two kernels run concurrently on two streams)
 
 // numpy pairwise sum of ld(0..len-1) computed by an aligned group of 8 lanes (lane j = accumulator j
@@ -316,7 +316,8 @@ struct KLaunch {
     static const char *range_name(int cls)
     {
         static const char *const names[nlf::P_NCLASS] = {"nlf:bandify", "nlf:diag_means+isotonic", "nlf:features", "nlf:forest",
-                                                         "nlf:threshold", "nlf:normalise", "nlf:pool", "nlf:score", "nlf:other"};
+                                                         "nlf:threshold", "nlf:normalise", "nlf:pool", "nlf:score", "nlf:isotonic", "nlf:count_candidates",
+                                                         "nlf:other"};
         return names[(cls >= 0 && cls < nlf::P_NCLASS) ? cls : nlf::P_NCLASS - 1];
     }
     KLaunch(nlf_ctx *ctx, int cls_, cudaStream_t st = nullptr) : c(ctx), cls(cls_), s(st ? st : ctx->stream)

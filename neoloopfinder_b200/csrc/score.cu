@@ -2347,11 +2347,11 @@ static int batch_prepare(nlf_batch *b)
         k_diag_means<<<grid, 256, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->pitch);
     }
     {
-        KLaunch k(c, P_DIAG);
+        KLaunch k(c, P_ISO);
         k_isotonic<<<nj, 128, (size_t)(b->upper + 2) * 20, c->stream>>>(b->d_jobs, b->lower, b->upper);
     }
     {
-        KLaunch k(c, P_THRESH);
+        KLaunch k(c, P_COUNT);
         dim3 grid(64, nj);
         k_count_candidates<<<grid, 256, 0, c->stream>>>(b->d_jobs, b->lower, b->upper, b->pitch);
     }
