@@ -615,10 +615,10 @@ def main():
         score_ms = prof["score"][0] / max(1, args.steps) if "score" in prof else 0.0
         # the dominant kernel by time: forest traversal (LSU / shared-memory bound), features (fp64-issue bound)
         # or, when the two run concurrently on the same SMs, the overlapped pair timed as one region
-        if score_ms > 0:
+        if score_ms > 0 and os.environ.get("NLF_SCORE_MODE") == "coop":
             dom, dom_ms = "k_features || k_forest_one (co-resident on every SM, timed together)", score_ms
         elif forest_ms >= feat_ms:
-            dom, dom_ms = "k_forest", forest_ms
+            dom, dom_ms = "k_forest_pipe (all launches of a step)", forest_ms
         else:
             dom, dom_ms = "k_features", feat_ms
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
