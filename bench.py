@@ -226,6 +226,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores():
+    """Cores this process may really use: loky's count honours CPU affinity and cgroup quotas (os.cpu_count() does not),
+    so the host-side worker pools are not oversubscribed on a box that exposes more cores than it grants."""
+    try:
+        from joblib import cpu_count
+        return max(1, int(cpu_count()))
+    except Exception:      # noqa: BLE001
+        return os.cpu_count() or 1
+
+
 def n_band_cells(n, upper=400, w=7):
     d = np.arange(0, min(n - 1, upper + 2 * w - 2) + 1)
     return int((n - d).sum())
@@ -250,7 +260,7 @@ def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
     from joblib import Parallel, delayed
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     config = wl.config(args.gpus)
     if wl.name == "cfg4":
         wl = Workload("cfg3", 0)          # the port has no banded input: its pixels/s is measured on 5 kb assembly matrices
@@ -464,7 +474,7 @@ def main():
     def sum_over_ranks(x):
         return reduce(x, dist.ReduceOp.SUM)
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     nproc = max(1, cores // world)
     ctx = _lib.Context.get(local_rank)
     forest = load_forest(MODEL, ctx)
@@ -687,6 +697,7 @@ def main():
                        "loops_per_step_rank0": n_loops, "band_cells_rank0": nband, "assemblies_rank0": len(host_mats)},
             "wall_ms_per_step_rank0": wall_ms / args.steps,
             "prep_seconds_rank0": {"pixel_table": table_s, "total_before_timing": prep_s},
+            "host": {"os_cpu_count": os.cpu_count(), "usable_cores": cores, "workers_per_rank": nproc},
         }
         if cli:
             line["cli_e2e"] = cli
