@@ -65,10 +65,11 @@ def _score_chunk(clr, live, assemblies, rsize, balance, prob, mmp, nopool, fores
         task_lists = [fu.regression_tasks() for _ID, fu in live]
         flat = [t for tl in task_lists for t in tl]
         if nproc > 1 and len(flat) > 8:
-            from joblib import Parallel, delayed
+            from functools import partial
+            from .util import run_parallel
             chunk = max(1, len(flat) // (nproc * 4))
             chunks = [flat[k:k + chunk] for k in range(0, len(flat), chunk)]
-            parts = Parallel(n_jobs=nproc)(delayed(_regress_chunk)(ch, expected) for ch in chunks)
+            parts = run_parallel(nproc, partial(_regress_chunk, expected=expected), chunks)
             fitted = [r for part in parts for r in part]
         else:
             fitted = _regress_chunk(flat, expected)

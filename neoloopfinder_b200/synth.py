@@ -183,6 +183,10 @@ def _assembly_pixels(clr, line, span):
     return (np.concatenate(keys), np.concatenate(vals)) if keys else (np.zeros(0, np.int64), np.zeros(0, np.int32))
 
 
+def _assembly_pixels_of(clr, span, line):
+    return _assembly_pixels(clr, line, span)
+
+
 def regional_pixel_cooler(clr, lines: Dict[str, str], span: int, nproc: int = 1):
     """A ``PixelCooler`` (cooler's pixel table, the format that lives in HBM) holding every pixel the
     assemblies in ``lines`` read from ``clr``: all block pairs of every assembly.  The rest of the
@@ -190,12 +194,9 @@ def regional_pixel_cooler(clr, lines: Dict[str, str], span: int, nproc: int = 1)
     the whole map; bins, chromosomes and weights are genome-wide as in a real ``.cool``.
     ``complexSV.reorganize_matrix`` reads the same values from it as from ``clr`` itself."""
     from .coolshim import PixelCooler
-    items = list(lines.values())
-    if nproc > 1 and len(items) > 1:
-        from joblib import Parallel, delayed
-        parts = Parallel(n_jobs=nproc)(delayed(_assembly_pixels)(clr, ln, span) for ln in items)
-    else:
-        parts = [_assembly_pixels(clr, ln, span) for ln in items]
+    from functools import partial
+    from .util import run_parallel
+    parts = run_parallel(nproc, partial(_assembly_pixels_of, clr, span), list(lines.values()))
     names = list(clr.chromnames)
     nb = [clr._nbins(c) for c in names]
     total = int(sum(nb))

@@ -20,6 +20,20 @@ def find_chrom_pre(chromlabels) -> str:
     return "chr" if chromlabels[0].startswith("chr") else ""
 
 
+def run_parallel(n_jobs, fn, items):
+    """[fn(x) for x in items] on ``n_jobs`` loky worker processes whose numeric libraries are held to ONE thread each.
+    The host work farmed out on this path (Huber / isotonic fits on <= 400 points, procedural pixel blocks) is far
+    too small for threaded BLAS; left alone, every worker starts cpu_count // n_jobs spinning OpenBLAS / OpenMP
+    threads, and with one such pool per GPU rank a box is oversubscribed many times over (8 ranks x 4 workers x 8
+    threads on 32 cores made a 2 s phase take minutes)."""
+    items = list(items)
+    if n_jobs <= 1 or len(items) <= 1:
+        return [fn(x) for x in items]
+    from joblib import Parallel, delayed, parallel_config
+    with parallel_config(backend="loky", inner_max_num_threads=1):
+        return Parallel(n_jobs=n_jobs)(delayed(fn)(x) for x in items)
+
+
 def autosomes(chromnames: Iterable[str]):
     """Chromosome filter of scripts/neoloop-caller:148-152 (drops names with _ M X Y MT EBV)."""
     keep = []
