@@ -638,8 +638,9 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-            if tr.get("workload") == wl.name and tr.get("assemblies") == len(host_mats):
-                traffic = tr["dram_bytes_per_step"]
+            if tr.get("workload") == wl.name and dom.startswith("k_forest_pipe"):
+                # ncu DRAM bytes of the forest launches per scored pixel (48-assembly capture of the same workload) x pixels
+                traffic = tr["k_forest_pipe"]["dram_bytes_per_scored_pixel"] * scored_per_step
         except (OSError, ValueError, KeyError):
             pass
         roofline = {
@@ -651,7 +652,9 @@ def main():
             "note": "The contract's HBM fraction on ALGORITHMIC bytes (8*N_band + 16*N_scored, SURVEY.md 8d) for the dominant "
                     "kernel(s).  It is small by construction (SURVEY.md D7: ~29 B but ~5k fp64 ops and ~1600 tree-node visits "
                     "per pixel): the binding resources are the fp64 pipe (roofline_fp64) and the shared-memory wavefront "
-                    "rate (roofline_smem); the HBM-bound band kernels are in roofline_band.",
+                    "rate (roofline_smem); the HBM-bound band kernels are in roofline_band.  traffic = ncu dram bytes of the "
+                    "forest launches per scored pixel (profiles/r02_traffic.json, 48-assembly capture) x scored pixels: the "
+                    "float32 features (676 B/pixel) are read once per forest part.",
         }
         fp64 = {
             "kernel": "k_features", "achieved_gops": alg_ops / (feat_ms * 1e-3) / 1e9 if feat_ms else None,

@@ -24,15 +24,18 @@ def main():
     total = sum(v[1] for v in agg.values())
     path_total = sum(v[1] for k, v in agg.items() if not k.startswith(PREP))
     print("# ncu launch list\n")
-    print("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 "
-          "--no-cpu-baseline` (plain run exited 0 first). First 400 launches of the process: untimed preparation "
-          "(normalisation of 50 assemblies), warm-up and timed steps. Per-launch times are cold-cache and serialised: "
-          "compare SHARES with the CUDA-event shares of the bench line, not absolute times.\n")
+    cmd = sys.argv[3] if len(sys.argv) > 3 else "python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+    print("`ncu --metrics gpu__time_duration.sum --clock-control none -c N --csv %s` (the plain command exited 0 first). "
+          "The first N launches of the process: untimed preparation (matrix assembly and normalisation from the pixel "
+          "table), warm-up and timed steps. Per-launch times are cold-cache and serialised: compare SHARES with the "
+          "CUDA-event shares of the bench line, not absolute times.\n" % cmd)
     if bench:
         d = json.loads(open(bench).read().strip().splitlines()[-1])
         k = d["kernels"]
         tot = sum(v["ms_per_step"] for v in k.values())
-        print("CUDA-event shares of the bench line (%s): " % bench.replace("gpurun_out/r01/bench.json", "profiles/r01_bench_b200.json") +
+        k = {n: v for n, v in k.items() if n != "score"}       # the score class is the feature + forest region, not a kernel
+        tot = sum(v["ms_per_step"] for v in k.values())
+        print("CUDA-event shares of the same command's bench line: " +
               ", ".join("%s %.2f ms = %.1f %%" % (n, v["ms_per_step"], 100 * v["ms_per_step"] / tot) for n, v in k.items()) +
               " of %.2f ms kernel time per step.\n" % tot)
     print("| kernel | launches | total us | share of all | share of scoring-path kernels |")
