@@ -164,15 +164,23 @@ def pipeline(clr, index, assemblies, rsize, balance, prob, mmp, nopool, models_b
                            expected)[index]
 
 
-def _device_worker(dev, clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, nproc, budget_mb):
-    """Body of one per-GPU worker process (or thread): its own CUDA context, forest copy and pixel table."""
+def _device_worker(dev, clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, nproc, budget_mb,
+                   child=False):
+    """Body of one per-GPU worker process (or thread): its own CUDA context, forest copy and pixel table.
+    ``child``: running in a spawned worker process, which must stop its own loky pool before it returns
+    (``util.shutdown_workers``)."""
     from . import _lib
-    ctx = _lib.Context.get(dev)
-    st = {}
-    r = call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, ctx, st, nproc,
-                        budget_mb)
-    st["launches"] = ctx.launch_count()
-    return r, st
+    try:
+        ctx = _lib.Context.get(dev)
+        st = {}
+        r = call_assemblies(clr, ids, assemblies, rsize, balance, prob, mmp, nopool, model_path, expected, ctx, st, nproc,
+                            budget_mb)
+        st["launches"] = ctx.launch_count()
+        return r, st
+    finally:
+        if child:
+            from .util import shutdown_workers
+            shutdown_workers()
 
 
 def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, nopool, model_path, expected,
@@ -221,7 +229,7 @@ def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, 
         from concurrent.futures import ProcessPoolExecutor
         with ProcessPoolExecutor(max_workers=len(jobs), mp_context=mp.get_context("spawn")) as ex:
             futs = [ex.submit(_device_worker, d, clr, mine, assemblies, rsize, balance, prob, mmp, nopool, model_path,
-                              expected, per_dev_nproc, budget_mb) for d, mine in jobs]
+                              expected, per_dev_nproc, budget_mb, True) for d, mine in jobs]
             per_dev = [f.result() for f in futs]
     for r, st in per_dev:
         results.update(r)

@@ -94,12 +94,17 @@ def call_chromosomes(clr, chroms: Sequence[str], model, expected, prob=0.9, min_
     return out
 
 
-def _genome_worker(dev, clr, chroms, model, expected, prob, min_count, no_pool, balance, upper):
+def _genome_worker(dev, clr, chroms, model, expected, prob, min_count, no_pool, balance, upper, child=False):
     from . import _lib
-    ctx = _lib.Context.get(dev)
-    st = {}
-    r = call_chromosomes(clr, chroms, model, expected, prob, min_count, no_pool, balance, ctx, st, upper)
-    return r, st
+    try:
+        ctx = _lib.Context.get(dev)
+        st = {}
+        r = call_chromosomes(clr, chroms, model, expected, prob, min_count, no_pool, balance, ctx, st, upper)
+        return r, st
+    finally:
+        if child:                      # a spawned worker stops its own loky pool before returning (util.shutdown_workers)
+            from .util import shutdown_workers
+            shutdown_workers()
 
 
 def call_genome(clr, model, expected, prob=0.9, min_count=2, no_pool=False, chroms: Optional[Iterable[str]] = None,
@@ -134,7 +139,7 @@ def call_genome(clr, model, expected, prob=0.9, min_count=2, no_pool=False, chro
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
         with ProcessPoolExecutor(max_workers=len(jobs), mp_context=mp.get_context("spawn")) as ex:
-            futs = [ex.submit(_genome_worker, d, src, cs, model, expected, prob, min_count, no_pool, balance, upper)
+            futs = [ex.submit(_genome_worker, d, src, cs, model, expected, prob, min_count, no_pool, balance, upper, True)
                     for d, cs in jobs]
             parts = [f.result() for f in futs]
     out = {}

@@ -48,11 +48,16 @@ def call_units(samples: Dict[str, dict], units: Sequence[Unit], rsize, balance, 
     return out
 
 
-def _sample_worker(dev, samples, units, rsize, balance, prob, mmp, nopool, nproc):
+def _sample_worker(dev, samples, units, rsize, balance, prob, mmp, nopool, nproc, child=False):
     from . import _lib
-    st = {}
-    r = call_units(samples, units, rsize, balance, prob, mmp, nopool, _lib.Context.get(dev), nproc, st)
-    return r, st
+    try:
+        st = {}
+        r = call_units(samples, units, rsize, balance, prob, mmp, nopool, _lib.Context.get(dev), nproc, st)
+        return r, st
+    finally:
+        if child:                      # a spawned worker stops its own loky pool before returning (util.shutdown_workers)
+            from .util import shutdown_workers
+            shutdown_workers()
 
 
 def call_samples(samples: Dict[str, dict], rsize, balance, prob, mmp, nopool, devices: Optional[List[int]] = None,
@@ -80,7 +85,7 @@ def call_samples(samples: Dict[str, dict], rsize, balance, prob, mmp, nopool, de
         from concurrent.futures import ProcessPoolExecutor
         with ProcessPoolExecutor(max_workers=len(jobs), mp_context=mp.get_context("spawn")) as ex:
             futs = [ex.submit(_sample_worker, d, {n: samples[n] for n in {name for name, _ in u}}, u, rsize, balance, prob,
-                              mmp, nopool, per_dev) for d, u in jobs]
+                              mmp, nopool, per_dev, True) for d, u in jobs]
             parts = [f.result() for f in futs]
     merged = {}
     for r, st in parts:

@@ -34,6 +34,19 @@ def run_parallel(n_jobs, fn, items):
         return Parallel(n_jobs=n_jobs)(delayed(fn)(x) for x in items)
 
 
+def shutdown_workers():
+    """Stop this process's loky worker pool now.  A per-GPU worker process (``cli.call_resolution`` and friends spawn
+    one per device) must do this before it returns: multiprocessing joins a child's non-daemonic children at exit, and
+    idle loky workers only leave after their 300 s timeout -- the parent would sit in ``shutdown()`` for five minutes."""
+    try:
+        from joblib.externals.loky import reusable_executor
+        ex = getattr(reusable_executor, "_executor", None)        # None: this process never started a pool
+        if ex is not None:
+            ex.shutdown(wait=True, kill_workers=True)
+    except Exception:      # noqa: BLE001 - nothing to stop
+        pass
+
+
 def autosomes(chromnames: Iterable[str]):
     """Chromosome filter of scripts/neoloop-caller:148-152 (drops names with _ M X Y MT EBV)."""
     keep = []

@@ -79,3 +79,14 @@ def pixel_cooler_from_fixture(z):
     np.cumsum(np.bincount(bin1, minlength=total), out=indptr[1:])
     sizes = {c: int(geo._chromsizes[c]) for c in names}
     return PixelCooler(res, sizes, indptr, (key - bin1 * total).astype(np.int32), val, {"weight": w, "sweight": w.copy()}), lines
+
+
+def pool_child(n, stop):
+    """Body of a spawned worker process that farms work out to its own loky pool (tests/test_host_boundary.py)."""
+    from neoloopfinder_b200.sharding import estimate_pixels
+    from neoloopfinder_b200.util import run_parallel, shutdown_workers
+    try:
+        return sum(run_parallel(2, estimate_pixels, range(400, 400 + n)))
+    finally:
+        if stop:
+            shutdown_workers()

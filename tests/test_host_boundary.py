@@ -93,3 +93,19 @@ def test_missing_weight_column_and_bad_regions_raise_like_cooler():
             clr.bins().fetch(("chr7", 0, 10))
     with pytest.raises(KeyError):
         px.device_pixels(object(), "sweight")
+
+
+def test_spawned_worker_with_its_own_pool_returns_at_once():
+    """One worker process per GPU (cli.call_resolution, genome.call_genome, multisample.call_samples) may farm its
+    regressions out to loky workers.  multiprocessing joins a child's children at exit and idle loky workers only
+    leave after 300 s, so such a worker must stop its pool itself (util.shutdown_workers): the executor closes in
+    seconds, not minutes."""
+    import multiprocessing as mp
+    import time
+    from concurrent.futures import ProcessPoolExecutor
+    from tests.helpers import pool_child
+    t0 = time.time()
+    with ProcessPoolExecutor(max_workers=2, mp_context=mp.get_context("spawn")) as ex:
+        got = [f.result() for f in [ex.submit(pool_child, 6, True) for _ in range(2)]]
+    assert got[0] == got[1] > 0
+    assert time.time() - t0 < 60
