@@ -483,7 +483,7 @@ def main():
     if wl.n_samples == 1:
         # one sample: the product's own sharder deals one fixed assembly list to the ranks
         lines = syn["S0"]["assemblies"]
-        units = [("S0", ID) for ID in shard_ids(list(lines), lines, SPAN, wl.res, world)[rank]]
+        units = [("S0", ID) for ID in shard_ids(list(lines), lines, SPAN, wl.res, world, syn["S0"]["clr"])[rank]]
     else:
         units = shard_sample_units(syn, SPAN, world)[rank]          # (sample, assembly) units over the ranks
     mine = {}

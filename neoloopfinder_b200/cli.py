@@ -204,7 +204,7 @@ def call_resolution(clr, assemblies: Dict[str, str], rsize, balance, prob, mmp, 
     ids = list(assemblies)
     res = clr.binsize
     # cost estimate from the assembly geometry only
-    weights = [assembly_weight(assemblies[ID], rsize, res) for ID in ids]
+    weights = [assembly_weight(assemblies[ID], rsize, res, clr) for ID in ids]
     shards = lpt_shards(weights, len(devices))
     jobs = [(d, [ids[k] for k in s]) for d, s in zip(devices, shards) if s]
     per_dev_nproc = max(1, nproc // max(1, len(jobs)))

@@ -26,7 +26,7 @@ def shard_sample_units(samples: Dict[str, dict], rsize: int, n_shards: int) -> L
         res = s["clr"].binsize
         for ID, line in s["assemblies"].items():
             units.append((name, ID))
-            weights.append(assembly_weight(line, rsize, res))
+            weights.append(assembly_weight(line, rsize, res, s["clr"]))
     shards = lpt_shards(weights, n_shards)
     return [[units[k] for k in sorted(shard)] for shard in shards]
 

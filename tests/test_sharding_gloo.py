@@ -104,6 +104,6 @@ def test_multi_sample_units_are_dealt_once_and_evenly():
     want = [(n, ID) for n, s in samples.items() for ID in s["assemblies"]]
     assert sorted(flat) == sorted(want) and len(set(flat)) == len(want)
     assert shards == shard_sample_units(samples, 3_000_000, 8)
-    w = {(n, ID): assembly_weight(s["assemblies"][ID], 3_000_000, 10000) for n, s in samples.items() for ID in s["assemblies"]}
+    w = {(n, ID): assembly_weight(s["assemblies"][ID], 3_000_000, 10000, s["clr"]) for n, s in samples.items() for ID in s["assemblies"]}
     loads = [sum(w[u] for u in s) for s in shards]
     assert max(loads) - min(loads) <= max(w.values())
