@@ -342,3 +342,25 @@ def test_multi_sample_batch_equals_per_sample_calls():
         assert got[name] == want, name
         n += sum(len(r) for r in want if r)
     assert n > 0 and stats["scored"] > 10000
+
+
+def test_sub_batches_do_not_change_results():
+    """call_assemblies works through an assembly file in sub-batches bounded by a device-memory budget (each one is
+    closed before the next is built); the split must not change any result."""
+    from neoloopfinder_b200.cli import call_assemblies
+    from neoloopfinder_b200.synth import SMALL_CHROMSIZES, analytic_expected
+    svs = [("chr2", 4_000_000, "-", "chr4", 3_000_000, "+"), ("chr1", 6_000_000, "+", "chr1", 8_000_000, "-")]
+    clr = SyntheticCooler(binsize=10000, chromsizes=SMALL_CHROMSIZES, seed=21, svs=svs)
+    lines = {
+        "C0": "translocation,2,4000000,-,4,3000000,+\t2,4500000\t4,2500000",
+        "C1": "deletion,1,6000000,+,1,8000000,-\t1,5500000\t1,8500000",
+        "C2": "duplication,1,5000000,-,1,5300000,+\t1,5800000\t1,4500000",     # invalid: costs no device memory
+    }
+    exp = analytic_expected(clr)
+    model = os.path.join(GOLDEN, "forest_w6.joblib")
+    s_one, s_many = {}, {}
+    one = call_assemblies(clr, list(lines), lines, 600000, "sweight", 0.3, 2, False, model, exp, stats=s_one)
+    many = call_assemblies(clr, list(lines), lines, 600000, "sweight", 0.3, 2, False, model, exp, stats=s_many, budget_mb=1)
+    assert one == many and one["C2"] is None
+    assert s_one["sub_batches"] == 1 and s_many["sub_batches"] == 2
+    assert s_one["scored"] == s_many["scored"] > 1000
