@@ -67,6 +67,14 @@ int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_off, const 
                       const int32_t *right, const int32_t *feature, const double *threshold,
                       const uint8_t *missing_left, const double *leaf_p1, int n_features,
                       nlf_forest **out);
+/* Host-only view of the compact single-pass forest (internal nodes only; csrc/score.cu k_forest_one) that
+ * nlf_forest_create builds next to the general node array: 1 = representable (arrays filled when the capacities
+ * suffice; NULL arrays = size query), 0 = not representable (the general kernels are used), < 0 = bad arguments.
+ * No CUDA call is made: exists so that the encoding can be checked against sklearn without a GPU. */
+int nlf_forest_compact_host(int n_trees, const int64_t *tree_off, const int32_t *left, const int32_t *right,
+                            const int32_t *feature, const double *threshold, const double *leaf_p1,
+                            long long cap_nodes, uint32_t *node_thr, uint32_t *node_word, long long cap_leaf,
+                            double *leafv, uint32_t *root, long long *n_int, long long *n_leaf);
 int nlf_forest_destroy(nlf_forest *f);
 /* predict_proba(X)[:, 1] for host float32 rows (N x n_features), results to proba[N]. */
 int nlf_forest_predict(nlf_forest *f, const float *X, long long N, double *proba);

@@ -45,6 +45,8 @@ _SIGNATURES = {
     "nlf_l2_flush": (C.c_int, [vp]),
     "nlf_fp64_peak": (C.c_int, [vp, dp]),
     "nlf_forest_create": (C.c_int, [vp, C.c_int, i64p, ip, ip, ip, dp, u8p, dp, C.c_int, C.POINTER(vp)]),
+    "nlf_forest_compact_host": (C.c_int, [C.c_int, i64p, ip, ip, ip, dp, dp, C.c_longlong, C.POINTER(C.c_uint32),
+                                           C.POINTER(C.c_uint32), C.c_longlong, dp, C.POINTER(C.c_uint32), llp, llp]),
     "nlf_forest_destroy": (C.c_int, [vp]),
     "nlf_forest_predict": (C.c_int, [vp, fp, C.c_longlong, dp]),
     "nlf_pixels_create": (C.c_int, [vp, C.c_longlong, i64p, ip, ip, dp, C.POINTER(vp)]),

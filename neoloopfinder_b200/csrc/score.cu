@@ -1614,6 +1614,121 @@ NLF_EXPORT int nlf_profile_read(nlf_ctx *c, int which, float *total_ms, long lon
 }
 
 // ---- forest -----------------------------------------------------------------------------------
+// Compact forest (k_forest_one): internal nodes only, depth-first with the IMPLICIT child right behind its parent.
+// Usable when thresholds and leaf values are non-negative and below 2 (the staged words keep their two top bits for
+// flags), there are at most 2048 distinct leaf values among the leaves of terminal nodes (11-bit references) and
+// every index fits its field.  Host only (no CUDA call): also exported for the CPU tests (nlf_forest_compact_host).
+static bool build_compact_forest(int n_trees, const int64_t *tree_off, const int32_t *left, const int32_t *right,
+                                 const int32_t *feature, const double *threshold, const double *leaf_p1,
+                                 std::vector<uint2> &nodes3, std::vector<double> &leafv3, std::vector<unsigned> &root3)
+{
+    const long long total = tree_off[n_trees];
+    nodes3.clear();
+    leafv3.clear();
+    root3.assign((size_t)n_trees, 0u);
+    bool v3_ok = true;
+    std::map<uint64_t, unsigned> leaf_ref;
+    auto ref_of = [&](long long node) -> unsigned {
+        const double v = leaf_p1[node];
+        uint64_t bits;
+        memcpy(&bits, &v, 8);
+        auto it = leaf_ref.find(bits);
+        if (it != leaf_ref.end()) return it->second;
+        const unsigned r = (unsigned)leafv3.size();
+        leaf_ref[bits] = r;
+        leafv3.push_back(v);
+        return r;
+    };
+    long long n_internal = 0;
+    for (long long k = 0; k < total; k++) {
+        if (left[k] >= 0) {
+            n_internal++;
+            if (!(threshold[k] >= 0.0 && threshold[k] < 2.0)) v3_ok = false;
+            if (feature[k] < 0 || feature[k] > 255) v3_ok = false;
+        } else if (!(leaf_p1[k] >= 0.0 && leaf_p1[k] < 2.0) || std::signbit(leaf_p1[k])) {
+            v3_ok = false;
+        }
+    }
+    if (n_internal >= (1 << 21)) v3_ok = false;
+    const unsigned LEAF = 0x80000000u;                 // marks "slot = n_internal + reference" until n_internal is final
+    struct Item { long long node; long long patch; };  // patch: compact index of the parent whose explicit field waits
+    std::vector<std::pair<unsigned, unsigned>> leaf_fix;   // (compact node, leaf reference) of explicit leaf children
+    for (int t = 0; t < n_trees && v3_ok; t++) {
+        const long long b = tree_off[t];
+        if (left[b] < 0) { root3[(size_t)t] = LEAF | ref_of(b); continue; }
+        root3[(size_t)t] = (unsigned)nodes3.size();
+        std::vector<Item> stack;
+        stack.push_back({b, -1});
+        while (!stack.empty()) {
+            const Item itx = stack.back();
+            stack.pop_back();
+            const long long k = itx.node;
+            const unsigned idx = (unsigned)nodes3.size();
+            if (itx.patch >= 0) nodes3[(size_t)itx.patch].y |= idx;
+            const long long L = b + left[k], R = b + right[k];
+            const bool lleaf = left[L] < 0, rleaf = left[R] < 0;
+            uint2 nd;
+            float tf = (float)threshold[k];
+            if ((double)tf > threshold[k]) tf = nextafterf(tf, -INFINITY);   // largest float <= threshold
+            memcpy(&nd.x, &tf, 4);
+            nd.y = ((unsigned)feature[k] & 0xffu) << 22;
+            if (lleaf && rleaf) {
+                const unsigned rl = ref_of(L), rr = ref_of(R);
+                if (rl >= 2048u || rr >= 2048u) { v3_ok = false; break; }
+                nd.y |= 0x40000000u | rl | (rr << 11);                 // terminal
+                nodes3.push_back(nd);
+            } else if (!lleaf && !rleaf) {
+                nd.y |= 0x80000000u;                                     // implicit left, explicit right (patched later)
+                nodes3.push_back(nd);
+                stack.push_back({R, (long long)idx});
+                stack.push_back({L, -1});                                // popped next: lands at idx + 1
+            } else if (rleaf) {
+                nd.y |= 0x80000000u;                                     // implicit left, explicit right leaf
+                nodes3.push_back(nd);
+                leaf_fix.push_back({idx, ref_of(R)});
+                stack.push_back({L, -1});
+            } else {
+                nd.y |= 0x80000000u | 0x40000000u;                       // S: the implicit child is the right one
+                nodes3.push_back(nd);
+                leaf_fix.push_back({idx, ref_of(L)});
+                stack.push_back({R, -1});
+            }
+        }
+    }
+    // explicit leaf children and one-leaf trees: slot = number of internal nodes + reference
+    const unsigned n_int = (unsigned)nodes3.size();
+    if (n_int + leafv3.size() >= (1u << 22) || leafv3.empty()) v3_ok = false;
+    if (v3_ok) {
+        for (auto &fx : leaf_fix) nodes3[fx.first].y |= n_int + fx.second;
+        for (auto &r : root3) if (r & LEAF) r = n_int + (r & ~LEAF);
+    }
+    return v3_ok;
+}
+
+// The compact forest on the host, for checking the encoding without a GPU: returns 1 and fills the arrays when the
+// forest is representable and the capacities suffice, 0 when it is not representable, < 0 on bad arguments.
+// node_thr[k] = float bits of the threshold, node_word[k] = packed word (see k_forest_one), root[t] = slot of the root.
+NLF_EXPORT int nlf_forest_compact_host(int n_trees, const int64_t *tree_off, const int32_t *left, const int32_t *right,
+                                       const int32_t *feature, const double *threshold, const double *leaf_p1,
+                                       long long cap_nodes, uint32_t *node_thr, uint32_t *node_word, long long cap_leaf,
+                                       double *leafv, uint32_t *root, long long *n_int, long long *n_leaf)
+{
+    if (n_trees <= 0 || !tree_off || !left || !right || !feature || !threshold || !leaf_p1 || !n_int || !n_leaf)
+        return fail(NLF_ERR_ARG, "nlf_forest_compact_host: bad arguments");
+    std::vector<uint2> nodes3;
+    std::vector<double> leafv3;
+    std::vector<unsigned> root3;
+    if (!build_compact_forest(n_trees, tree_off, left, right, feature, threshold, leaf_p1, nodes3, leafv3, root3)) return 0;
+    *n_int = (long long)nodes3.size();
+    *n_leaf = (long long)leafv3.size();
+    if (!node_thr || !node_word || !leafv || !root) return 1;                 // size query
+    if (cap_nodes < *n_int || cap_leaf < *n_leaf) return fail(NLF_ERR_ARG, "nlf_forest_compact_host: capacity too small");
+    for (size_t k = 0; k < nodes3.size(); k++) { node_thr[k] = nodes3[k].x; node_word[k] = nodes3[k].y; }
+    for (size_t k = 0; k < leafv3.size(); k++) leafv[k] = leafv3[k];
+    for (int t = 0; t < n_trees; t++) root[t] = root3[(size_t)t];
+    return 1;
+}
+
 NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_off, const int32_t *left,
                                  const int32_t *right, const int32_t *feature, const double *threshold,
                                  const uint8_t *missing_left, const double *leaf_p1, int n_features,
@@ -1673,88 +1788,11 @@ NLF_EXPORT int nlf_forest_create(nlf_ctx *ctx, int n_trees, const int64_t *tree_
             nodes2[(size_t)(b + k)] = nd;
         }
     }
-    // compact format: internal nodes only, depth-first with the IMPLICIT child right behind its parent
-    // (see k_forest_one).  Usable when thresholds and leaf values are non-negative and below 2 (the staged
-    // words keep their two top bits for flags), there are at most 2048 distinct leaf values (11-bit
-    // references in terminal nodes) and every index fits its field.
+    // compact format (k_forest_one): internal nodes only, see build_compact_forest
     std::vector<uint2> nodes3;
     std::vector<double> leafv3;
-    std::vector<unsigned> root3((size_t)n_trees);
-    bool v3_ok = true;
-    {
-        std::map<uint64_t, unsigned> leaf_ref;
-        auto ref_of = [&](long long node) -> unsigned {
-            const double v = leaf_p1[node];
-            uint64_t bits;
-            memcpy(&bits, &v, 8);
-            auto it = leaf_ref.find(bits);
-            if (it != leaf_ref.end()) return it->second;
-            const unsigned r = (unsigned)leafv3.size();
-            leaf_ref[bits] = r;
-            leafv3.push_back(v);
-            return r;
-        };
-        long long n_internal = 0;
-        for (long long k = 0; k < total; k++) {
-            if (left[k] >= 0) {
-                n_internal++;
-                if (!(threshold[k] >= 0.0 && threshold[k] < 2.0)) v3_ok = false;
-            } else if (!(leaf_p1[k] >= 0.0 && leaf_p1[k] < 2.0) || std::signbit(leaf_p1[k])) {
-                v3_ok = false;
-            }
-        }
-        if (n_internal >= (1 << 21)) v3_ok = false;
-        const unsigned LEAF = 0x80000000u;                 // marks "slot = n_internal + reference" until n_internal is final
-        struct Item { long long node; long long patch; };  // patch: compact index of the parent whose explicit field waits
-        std::vector<std::pair<unsigned, unsigned>> leaf_fix;   // (compact node, leaf reference) of explicit leaf children
-        for (int t = 0; t < n_trees && v3_ok; t++) {
-            const long long b = tree_off[t];
-            if (left[b] < 0) { root3[(size_t)t] = LEAF | ref_of(b); continue; }
-            root3[(size_t)t] = (unsigned)nodes3.size();
-            std::vector<Item> stack;
-            stack.push_back({b, -1});
-            while (!stack.empty()) {
-                const Item itx = stack.back();
-                stack.pop_back();
-                const long long k = itx.node;
-                const unsigned idx = (unsigned)nodes3.size();
-                if (itx.patch >= 0) nodes3[(size_t)itx.patch].y |= idx;
-                const long long L = b + left[k], R = b + right[k];
-                const bool lleaf = left[L] < 0, rleaf = left[R] < 0;
-                uint2 nd;
-                nd.x = nodes[(size_t)k].x;                                  // largest float <= threshold
-                nd.y = ((unsigned)feature[k] & 0xffu) << 22;
-                if (lleaf && rleaf) {
-                    const unsigned rl = ref_of(L), rr = ref_of(R);
-                    if (rl >= 2048u || rr >= 2048u) { v3_ok = false; break; }
-                    nd.y |= 0x40000000u | rl | (rr << 11);                 // terminal
-                    nodes3.push_back(nd);
-                } else if (!lleaf && !rleaf) {
-                    nd.y |= 0x80000000u;                                     // implicit left, explicit right (patched later)
-                    nodes3.push_back(nd);
-                    stack.push_back({R, (long long)idx});
-                    stack.push_back({L, -1});                                // popped next: lands at idx + 1
-                } else if (rleaf) {
-                    nd.y |= 0x80000000u;                                     // implicit left, explicit right leaf
-                    nodes3.push_back(nd);
-                    leaf_fix.push_back({idx, ref_of(R)});
-                    stack.push_back({L, -1});
-                } else {
-                    nd.y |= 0x80000000u | 0x40000000u;                       // S: the implicit child is the right one
-                    nodes3.push_back(nd);
-                    leaf_fix.push_back({idx, ref_of(L)});
-                    stack.push_back({R, -1});
-                }
-            }
-        }
-        // explicit leaf children and one-leaf trees: slot = number of internal nodes + reference
-        const unsigned n_int = (unsigned)nodes3.size();
-        if (n_int + leafv3.size() >= (1u << 22) || leafv3.empty()) v3_ok = false;
-        if (v3_ok) {
-            for (auto &fx : leaf_fix) nodes3[fx.first].y |= n_int + fx.second;
-            for (auto &r : root3) if (r & LEAF) r = n_int + (r & ~LEAF);
-        }
-    }
+    std::vector<unsigned> root3;
+    const bool v3_ok = build_compact_forest(n_trees, tree_off, left, right, feature, threshold, leaf_p1, nodes3, leafv3, root3);
     NLF_CUDA(cudaSetDevice(ctx->device));
     nlf_forest *f = new nlf_forest();
     f->ctx = ctx;
