@@ -250,16 +250,17 @@ class complexSV(Fusion):
                 row = mean[p]
                 p += 1
                 kept = np.where(~np.isnan(row))[0]
+                kept_keys = kept.tolist()
+                kept_vals = list(row[kept])                  # numpy float64 scalars, as row[i] gives them
                 memo, steps = {}, []
                 local_exp = {}
                 for maxdis in _MAXDIS_LADDER:
-                    upto = kept[kept <= maxdis // res]
-                    local_exp = {int(i): row[i] for i in upto}
-                    key = len(upto)                      # prefixes: same length <=> same dictionary
+                    key = int(np.searchsorted(kept, maxdis // res, side="right"))     # prefixes: same length <=> same dictionary
                     if key not in memo:
                         memo[key] = len(tasks)
-                        tasks.append(local_exp)
+                        tasks.append(dict(zip(kept_keys[:key], kept_vals[:key])))
                     steps.append(memo[key])
+                    local_exp = tasks[memo[key]]
                 self._reg_plan.append((j1, j2, steps, local_exp))
         return tasks
 
