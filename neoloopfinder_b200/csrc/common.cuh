@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -95,6 +96,10 @@ __device__ double np_pairwise_sum_group8(Load ld, int len, int j, unsigned gmask
 }  // namespace nlf
 
 struct nlf_ctx {
+    // Host-side caches below (big buffers, staging ring, event pool, profiling records, launch counter) are guarded
+    // by this mutex, so two host threads that end up on the same context (e.g. a device listed twice) cannot hand
+    // one buffer to two users.  Work of one context is still ordered on its single main stream.
+    std::recursive_mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -118,6 +123,7 @@ struct nlf_ctx {
     // main-stream order (big_free records an event there); another stream waits for that event.
     cudaError_t big_alloc(void **out, size_t bytes, cudaStream_t consumer = nullptr)
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         int best = -1;
         for (int i = 0; i < (int)bigs.size(); i++)
             if (!bigs[i].busy && bigs[i].bytes >= bytes && bigs[i].bytes <= bytes + bytes / 4 + (1 << 20) &&
@@ -148,6 +154,7 @@ struct nlf_ctx {
     }
     void big_free(void *p)
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         if (!p) return;
         for (auto &b : bigs)
             if (b.p == p) {
@@ -159,6 +166,7 @@ struct nlf_ctx {
     }
     void big_release_all()
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         for (auto &b : bigs) { if (b.p) cudaFree(b.p); if (b.freed) cudaEventDestroy(b.freed); }
         bigs.clear();
     }
@@ -175,6 +183,7 @@ struct nlf_ctx {
     cudaEvent_t ev_feat[NEVT] = {nullptr}, ev_forest[NEVT] = {nullptr};   // per feature-buffer set (re-recorded every use)
     cudaError_t aux_init()
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         if (aux_stream) return cudaSuccess;
         int lo = 0, hi = 0;
         cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -202,6 +211,7 @@ struct nlf_ctx {
     // order the copy stream after everything enqueued on the main stream so far
     cudaError_t copy_fence()
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         cudaError_t e;
         if (!fence && (e = cudaEventCreateWithFlags(&fence, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(fence, stream)) != cudaSuccess) return e;
@@ -210,6 +220,7 @@ struct nlf_ctx {
     // a staging buffer of at least `bytes`, safe to overwrite from the copy stream
     cudaError_t stage_acquire(size_t bytes, void **dev)
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         Stage &s = stages[stage_next];
         stage_next = (stage_next + 1) % NSTAGE;
         cudaError_t e;
@@ -235,11 +246,13 @@ struct nlf_ctx {
     }
     void stage_release(void *dev)
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         for (auto &s : stages)
             if (s.p == dev) { cudaEventRecord(s.used, copy_stream); s.pending = true; return; }
     }
     void stage_release_all()
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         for (auto &s : stages) {
             if (s.p) cudaFree(s.p);
             if (s.used) cudaEventDestroy(s.used);
@@ -251,6 +264,7 @@ struct nlf_ctx {
 
     cudaEvent_t get_event()
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
         cudaEvent_t e;
         cudaEventCreate(&e);
@@ -258,6 +272,7 @@ struct nlf_ctx {
     }
     void prof_begin(int cls, cudaEvent_t *a, cudaStream_t s)
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         launches++;
         if (!profile) return;
         *a = get_event();
@@ -266,6 +281,7 @@ struct nlf_ctx {
     }
     void prof_end(int cls, cudaEvent_t a, cudaStream_t s)
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         if (!profile) return;
         cudaEvent_t b = get_event();
         cudaEventRecord(b, s);
@@ -273,6 +289,7 @@ struct nlf_ctx {
     }
     void prof_resolve()
     {
+        std::lock_guard<std::recursive_mutex> lock(mu);
         static const bool trace = getenv("NLF_TRACE") != nullptr;     // per-launch timeline on stderr (tuning)
         for (auto &r : recs) {
             float ms = 0;
